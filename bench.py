@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — doc-tokens/sec per full variational-inference EM iteration (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg3] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is ONE full EM iteration of the hot path over the resident corpus: E-step (gamma + theta refresh),
+K x V sufficient statistics, [NCCL all-reduce of the statistics when N > 1], M-step (lambda + beta refresh), the
+ELBO token term and the device->host read of the perplexity terms — exactly what LDASmoothed.fit does per
+iteration.  Workload at N=1: BASELINE.json configs[2] "synthetic 1M docs x 300 tokens, K=100, V=50k" (cfg3), the
+configuration the 60 %-of-roofline target is quoted on; for N > 1 every rank holds its own cfg3-sized document
+shard (weak scaling), lambda is replicated and the statistics are summed with one fp64 all-reduce per iteration.
+
+Prints ONE JSON line (rank 0).  `value` is the device-timed whole-job throughput with the corpus resident in HBM;
+`e2e` repeats the measurement through the public API with the CSR corpus coming from pinned HOST memory every
+step (H2D copy + CSC rebuild + EM iteration + D2H of the result inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "doc_tokens_per_sec_per_em_iteration"
+UNIT = "doc-tokens/s"
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(nnz, D, K, V):
+    """Gather-model bytes.  Per launch of each kernel and per EM iteration."""
+    kb = 8 * K
+    est = nnz * (kb + 8) + D * kb * 4 + (D + 1) * 8      # gather eB row + (colidx,count); eT in, gamma in/out, eT out
+    sst = nnz * (kb + 8) + V * kb * 2 + (V + 1) * 8      # gather eT row + (docidx,count); eB in, S out
+    mst = V * kb * 6                                       # S, eB in; lambda out; lambda in; eB out (+colsum pass)
+    elb = nnz * (kb + 8) + D * kb + (D + 1) * 8            # gather eB row + (colidx,count); eT in
+    return {"ttlda_estep_f64": est, "ttlda_sstats_csc_f64": sst, "ttlda_mstep_f64": mst,
+            "ttlda_elbo_tokens_f64": elb, "iteration": est + sst + mst + elb}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def committed_traffic(kernel, config):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json), else None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p)).get(config, {}).get(kernel)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (oracle/lda_oracle.c, gcc + OpenMP, all host threads) on a bounded sample
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_port_iteration_time(rp, ci, ct, K, V, steps, warmup):
+    """Seconds per full EM iteration (E-step + M-step + ELBO/perplexity) of the CPU oracle on the given CSR sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    from lda_oracle import CSRCorpus, OracleLDA, c_num_threads
+
+    X = CSRCorpus(rp, ci, ct, V)
+    m = OracleLDA(K, engine="c")
+    m.M, m.V = X.D, V
+    np.random.seed(42)
+    m.lam = np.random.gamma(100., 0.01, (K, V))
+    m.gamma = np.ascontiguousarray(np.full((X.D, K), 1.0 + V / K))
+    _, logs = m.approx_perplexity(X)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        et, eb = m.em_step(X, logs[0], logs[1])
+        _, logs = m.approx_perplexity(X, False, et, eb)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), c_num_threads(), X.tokens
+
+
+def run_reference(args):
+    """--impl reference: the reference's algorithm on the host cores (oracle port; the Python reference itself
+    cannot travel to the GPU box and manages ~7e3 doc-tokens/s)."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from tuotuo_b200.synth import CONFIGS, synthetic_token_stream
+
+    D, L, K, V, pois = CONFIGS[args.config]
+    n = min(D, args.cpu_docs)
+    tok, offs = synthetic_token_stream(n, L, K, V, device="cpu", seed=1234, poisson=pois)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from lda_oracle import CSRCorpus
+
+    X = CSRCorpus.from_token_ids(tok.numpy(), offs.numpy(), V)
+    sec, threads, tokens = cpu_port_iteration_time(X.rowptr, X.colidx, X.counts, K, V, args.steps, args.warmup)
+    val = tokens / sec
+    sample = f"{n} of {D} documents of {args.config} (same generator, K={K}, V={V}), full EM iteration incl. the K*V M-step"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {sample}", "K": K, "V": V, "docs": n, "doc_tokens": tokens},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tuotuo_b200 import _native as nv
+    from tuotuo_b200.lda_model import LDASmoothed
+    from tuotuo_b200.synth import CONFIGS, synthetic_document
+
+    D, L, K, V, pois = CONFIGS[args.config]
+    if args.docs:
+        D = args.docs
+    doc = synthetic_document(args.config, device=dev, seed=1234 + rank, docs=D)
+    lda = LDASmoothed(K, verbose=False, device=dev, sstats_mode=args.sstats)
+    # em_num_step=0: corpus upload/CSR+CSC build, lambda_0 / gamma_0 initialisation, initial perplexity (untimed)
+    p0 = lda.fit(doc, em_num_step=0, update_hyper_parms=False, return_perplexities=True)
+    st = lda._st
+    c = st.corpus
+    tokens_local, nnz_local = c.tokens, c.nnz
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step():
+        lda._em_iteration(e_num_step=100)
+        lda._collect(theta_row=0)
+        return lda._perplexity_from_terms(False)
+
+    perps = [float(p0[0])]
+    for _ in range(args.warmup):
+        perps.append(one_step())
+
+    # ---- timed region: value --------------------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    nv.timing = {}
+    k0 = nv.kernel_count
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        perps.append(one_step())
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = nv.kernel_count - k0
+    ms = e0.elapsed_time(e1)
+    per_kernel = {n: sum(a.elapsed_time(b) for a, b in ev) / len(ev) for n, ev in nv.timing.items()}
+    nv.timing = None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([tokens_local, nnz_local, c.D], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot)
+    ms = float(t.item())
+    tokens_all, nnz_all, docs_all = (int(x) for x in tot.tolist())
+    ms_per_step = ms / args.steps
+    value = tokens_all / (ms_per_step * 1e-3)
+
+    # ---- e2e: CSR corpus arrives from pinned host memory every step ---------------------------------------------------
+    h_rp, h_ci, h_ct = (x.cpu().pin_memory() for x in (c.rowptr, c.colidx, c.counts))
+    h2d = h_rp.numel() * 8 + h_ci.numel() * 4 + h_ct.numel() * 4
+
+    def e2e_step():
+        c.rowptr.copy_(h_rp, non_blocking=True)
+        c.colidx.copy_(h_ci, non_blocking=True)
+        c.counts.copy_(h_ct, non_blocking=True)
+        c.build_csc()
+        return one_step()
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    n_e2e = max(2, min(args.steps, 5))
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(n_e2e):
+        e2e_step()
+    f1.record()
+    barrier()
+    t2 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t2.item()) / n_e2e
+    e2e_val = tokens_all / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel --------------------------------------------------------------------------------------
+    ab = algorithmic_bytes(nnz_local, c.D, K, V)
+    peak, peak_src = measured_peaks()
+    hot = {k: v for k, v in per_kernel.items() if k in ab}
+    dom = max(hot, key=hot.get)
+    dom_ms = hot[dom]
+    achieved = ab[dom] / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": committed_traffic(dom, args.config), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": ab[dom], "kernel_ms": dom_ms,
+                "kernel_ms_all": {k: round(v, 4) for k, v in per_kernel.items()},
+                "iteration_frac": ab["iteration"] / (ms_per_step * 1e-3) / 1e9 / peak,
+                "note": "gathers of the 8*K*V-byte exp(E[log beta]) table are L2 hits when it fits the 126 MB L2"}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        n = min(c.D, args.cpu_docs)
+        rp = c.rowptr[:n + 1].cpu().numpy()
+        e = int(rp[-1])
+        sec, threads, tok = cpu_port_iteration_time(rp, c.colidx[:e].cpu().numpy(), c.counts[:e].cpu().numpy(), K, V,
+                                                    2, 1)
+        cpu = {"value": tok / sec, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"first {n} of {c.D} documents of rank 0's {args.config} shard, 2 timed EM iterations of "
+                         f"oracle/lda_oracle.c (gcc -O2 -fopenmp), {os.cpu_count()} host CPUs visible",
+               "ms_per_step": sec * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{args.config}: {docs_all} docs x ~{L} tokens, K={K}, V={V} "
+                                       f"({docs_all // world} docs per GPU), batch VI EM iteration",
+                           "docs": docs_all, "doc_tokens": tokens_all, "nnz": nnz_all, "K": K, "V": V,
+                           "parallelism": f"doc-shard x{world}" + (" + NCCL all-reduce(K*V f64)" if world > 1 else ""),
+                           "sstats": args.sstats,
+                           "l2": "no explicit flush: each step streams the CSR/CSC arrays and the D*K theta tables "
+                                 f"({(c.nbytes() + 3 * c.D * K * 8) / 1e9:.1f} GB per GPU) >> 126 MB L2"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 48 * world,
+                        "ms_per_step": e2e_ms, "steps": n_e2e,
+                        "what": "pinned-host CSR -> device, CSC rebuild, EM iteration, perplexity terms -> host"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "perplexity_trace": [round(p, 6) for p in perps[:8]]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3")
+    ap.add_argument("--docs", type=int, default=0, help="override documents per GPU (debug)")
+    ap.add_argument("--sstats", default="csc", choices=["csc", "atomic"])
+    ap.add_argument("--cpu-docs", type=int, default=20000, help="documents in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: W >= 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+/*
+ * ttlda.h — C ABI of libttlda.so: the sm_100a kernels behind TuoTuo's batch variational-inference LDA hot path.
+ *
+ * This is the drop-in boundary.  The reference exposes its only native code as the CPython
+ * extension `tuotuo.cutils` (tuotuo/cutils.pyx:11-93, built by setup.py:18-27); everything else on the path is
+ * NumPy/SciPy inside `tuotuo/lda_model.py`.  Each entry point below names the reference interface it replaces.
+ *
+ * Conventions (every function):
+ *   - plain C types only; all array arguments are DEVICE pointers owned by the caller (e.g. torch
+ *     `Tensor.data_ptr()`), `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - asynchronous on `stream`; never allocates, frees or synchronises; scratch space is caller-provided and
+ *     sized by the matching `*_workspace_bytes` query;
+ *   - returns 0 (TTLDA_OK) or a negative TTLDA_E* code; `ttlda_last_error()` gives the message (thread-local);
+ *   - all floating point is IEEE double ("f64"), all results are bit-reproducible run to run unless a function
+ *     says otherwise; indices are bit-exact.
+ *
+ * Device layouts ("word-major", chosen for coalesced K-vector gathers — DESIGN.md §3):
+ *   ld            leading dimension of every K-vector table: K rounded up to a multiple of 4 (32-byte rows)
+ *   theta tables  gamma, exp_elogtheta           [D][ld]   row d = document d        (reference: (M,K))
+ *   beta tables   lambda, exp_elogbeta, sstats   [V][ld]   row w = vocabulary id w   (reference: (K,V) — transposed)
+ *   padding columns k in [K, ld) hold 0 in exp_* tables and sstats and are ignored elsewhere.
+ *   CSR corpus    rowptr int64[D+1], colidx int32[nnz] ascending within a row, counts int32[nnz]
+ *   CSC mirror    colptr int64[V+1], docidx int32[nnz] ascending within a column, ccounts int32[nnz]
+ */
+#ifndef TTLDA_H
+#define TTLDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TTLDA_OK 0
+#define TTLDA_EINVAL (-1)   /* bad argument (NULL pointer, K out of range, ld not a multiple of 4, ...) */
+#define TTLDA_ECUDA (-2)    /* a CUDA runtime call / kernel launch failed; see ttlda_last_error() */
+#define TTLDA_EWORKSPACE (-3) /* workspace too small */
+#define TTLDA_EARCH (-4)    /* device is not sm_100 */
+
+#define TTLDA_MAX_K 1024 /* topics per model supported by the register-resident E-step */
+#define TTLDA_NPART 8    /* doubles per partial-sum record written by the reduction kernels */
+
+/* library ------------------------------------------------------------------------------------------------ */
+int ttlda_version(void);                 /* (major<<16)|(minor<<8)|patch */
+const char* ttlda_last_error(void);      /* message of the last failing call on this thread ("" if none) */
+int ttlda_check_device(int device);      /* TTLDA_OK iff `device` is compute capability 10.x */
+int64_t ttlda_ld_for(int64_t K);         /* the leading dimension the kernels require for K topics */
+
+/*
+ * Row-wise Dirichlet expectation with the reference's AS-103 digamma.
+ * Replaces: tuotuo.cutils._dirichlet_expectation_2d (tuotuo/cutils.pyx:41-68) and psi (:75-93); with
+ * out_exp != NULL also the np.exp(...) applied to its result at tuotuo/lda_model.py:232-233,264.
+ *   a [rows][ld] (first `cols` entries of each row are used);  out_elog / out_exp [rows][ld], either may be NULL.
+ */
+int ttlda_dirichlet_expectation_f64(const double* a, int64_t rows, int64_t cols, int64_t ld,
+                                    double* out_elog, double* out_exp, void* stream);
+
+/*
+ * In-place variant of the single-sample form.
+ * Replaces: tuotuo.cutils._dirichlet_expectation_1d (tuotuo/cutils.pyx:11-38):
+ *   doc_topic[i] += prior;  out[i] = exp(psi~(doc_topic[i]) - psi~(sum_i doc_topic[i])).
+ */
+int ttlda_dirichlet_expectation_1d_f64(double* doc_topic, double prior, double* out, int64_t size, void* stream);
+
+/*
+ * Bag-of-words: token-id stream -> CSR doc-term matrix (sorted unique word ids per document + counts).
+ * Replaces: the count matrix built by get_vocab_from_docs / get_np_wct (tuotuo/utils.py:177-206) and exposed as
+ * Document.doc_vocab_count_array (tuotuo/document.py:33-36); the rows equal np.nonzero(X[d,:]) / X[d, ids].
+ *   token_ids int32[T] (vocabulary ids, 0 <= id < V), doc_offsets int64[D+1] (token ranges per document).
+ *   Outputs: rowptr int64[D+1], colidx/counts int32[>= T] (first *nnz entries valid), nnz_out int64[1] (device).
+ */
+int64_t ttlda_bow_to_csr_workspace_bytes(int64_t T, int64_t D, int64_t V);
+int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64_t T, int64_t D, int64_t V,
+                     int64_t* rowptr, int32_t* colidx, int32_t* counts, int64_t* nnz_out,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* CSR -> CSC mirror (stable: documents ascending within each word).  No reference counterpart: the dense
+ * matrix of tuotuo/document.py:36 is addressable both ways; the CSC copy gives the M-step the same access. */
+int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V);
+int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                     int64_t D, int64_t V, int64_t nnz,
+                     int64_t* colptr, int32_t* docidx, int32_t* ccounts,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * theta refresh: exp_elogtheta = exp(dirichlet_expectation(gamma)) and the theta-prior ELBO term.
+ * Replaces: _dirichlet_expectation_2d(self._gamma_) at tuotuo/lda_model.py:116,256 (+ np.exp at :232) and
+ * expec_real_dist_minus_suro_dist(Elogtheta, alpha, gamma) (:25-46, call site :142-148).
+ *   alpha_vec double[K] on device (a scalar prior is broadcast by the caller); alpha_sum = np.sum(alpha) as the
+ *   reference evaluates it (the scalar itself for a scalar prior — SURVEY.md §8 a7).
+ *   partial_out double[TTLDA_NPART] (device): [0] = theta-prior term, rest 0.  exp_elogtheta may be NULL.
+ */
+int64_t ttlda_reduce_workspace_bytes(void);
+int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t ld,
+                            const double* alpha_vec, double alpha_sum,
+                            double* exp_elogtheta, double* partial_out,
+                            void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * E-step, document-major pass (one warp per document, K topics in registers).
+ * Replaces: LDASmoothed.e_step (tuotuo/lda_model.py:197-270) for gamma, plus — fused — the per-token ELBO term
+ * of approx_elbo (:125-139) evaluated at the *incoming* state and the theta-prior term (:142-148) and theta
+ * refresh (:256) at the *outgoing* state.  Per document d with words w, counts c:
+ *      N_dw = sum_k eT_in[d,k]*eB[w,k] (+1e-100 in the normaliser, :242);  gamma[d,k] = alpha_k + eT_in[d,k] *
+ *      sum_w (c_dw/N_dw) eB[w,k] (:248);  eT_out[d,:] = exp(dirichlet_expectation(gamma[d,:])).
+ * `max_iter`/`tol` restate the reference's while-loop (:236): because exp(Elogtheta_d) is frozen inside it, the
+ * update is idempotent and the loop exits on its second pass; the kernel evaluates the update once and reports
+ * `iters_out[0]` = sum over documents of the passes the reference would have made, `iters_out[1]` = documents
+ * that hit the cap (`it > max_iter`, warned about at :258-259).
+ *   sstats_atomic: if non-NULL, also scatters sstats[w,k] += eT_in[d,k]*c/N with red.global.add.f64 (the
+ *   one-pass alternative to ttlda_sstats_csc_f64; not bit-reproducible).  Must be zeroed by the caller.
+ *   partial_out double[TTLDA_NPART]: [0] token term at the incoming state, [1] theta-prior term at the outgoing
+ *   state, [2] sum of counts.
+ */
+int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                    int64_t D, int64_t K, int64_t V, int64_t ld,
+                    const double* alpha_vec, double alpha_sum,
+                    const double* exp_elogtheta_in, const double* exp_elogbeta,
+                    double* gamma, double* exp_elogtheta_out, double* sstats_atomic,
+                    int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * M-step sufficient statistics, word-major pass over the CSC mirror (no atomics, no phi in HBM):
+ *      sstats[w,k] = sum_{d: X_dw>0} eT[d,k] * c_dw / (sum_k' eT[d,k'] eB[w,k'] + 1e-100)
+ * Replaces: lambda_update[:, ids] += np.outer(eT, cts/phi_norm) at tuotuo/lda_model.py:262 (the trailing
+ * `*= exp(Elogbeta)` of :264 is applied by ttlda_mstep_f64, after the cross-GPU sum — it is linear).
+ */
+int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld);
+int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts,
+                         int64_t V, int64_t K, int64_t ld, int64_t nnz,
+                         const double* exp_elogtheta, const double* exp_elogbeta, double* sstats,
+                         void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * M-step: lambda = eta + sstats * exp_elogbeta;  exp_elogbeta <- exp(dirichlet_expectation(lambda));
+ * beta-prior ELBO term at the new lambda.
+ * Replaces: lambda_update *= np.exp(expec_log_beta) (tuotuo/lda_model.py:264), LDASmoothed.m_step (:273-283)
+ * and expec_real_dist_minus_suro_dist(Elogbeta, eta, lambda) (:157-163).
+ *   lambda [V][ld] out; exp_elogbeta [V][ld] in/out; elogbeta_out may be NULL; colsum_out double[ld] = sum_w lambda[w,k].
+ *   partial_out double[TTLDA_NPART]: [0] = beta-prior term.
+ */
+int64_t ttlda_mstep_workspace_bytes(int64_t V, int64_t ld);
+int ttlda_mstep_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, double eta,
+                    double* exp_elogbeta, double* lambda, double* elogbeta_out, double* colsum_out,
+                    double* partial_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* beta refresh from an existing lambda (initial state, or after a hyper-parameter update):
+ * exp_elogbeta = exp(dirichlet_expectation over the vocabulary of lambda[:,k]) and the beta-prior term.
+ * Replaces: _dirichlet_expectation_2d(self._lambda_) at tuotuo/lda_model.py:120 and the term at :157-163. */
+int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t ld, double eta,
+                           double* exp_elogbeta, double* elogbeta_out, double* colsum_out,
+                           double* partial_out, void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Token term of the ELBO: sum_d sum_w c_dw * log(sum_k eT[d,k]*eB[w,k])  (= logsumexp_k(Elogtheta+Elogbeta)).
+ * Replaces: the double loop over documents and words of approx_elbo, tuotuo/lda_model.py:125-139.
+ *   partial_out double[TTLDA_NPART]: [0] token term, [2] sum of counts.
+ */
+int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                          int64_t D, int64_t K, int64_t ld,
+                          const double* exp_elogtheta, const double* exp_elogbeta, double* partial_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
+ * Newton statistics for the hyper-parameter updates, with an EXACT digamma (the reference calls
+ * scipy.special.psi here, not AS-103): out[0] = sum_ij psi(x_ij), out[1] = sum_i psi(sum_j x_ij) over the
+ * first `cols` entries of each of `rows` rows of x [rows][ld].
+ * Replaces: psi(self._gamma_) / psi(np.sum(self._gamma_,1)) at tuotuo/lda_model.py:449-462 and the lambda
+ * analogue at :522-528 (for the word-major lambda pass cols=K and use out[0] with ttlda_psi_f64 on colsum).
+ */
+int ttlda_hyper_stats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* partial_out,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int ttlda_psi_f64(const double* x, int64_t n, double* out, void* stream); /* exact digamma, elementwise, x > 0 */
+
+/* layout helpers between the reference's (K,V) topic-major matrices and the word-major device tables */
+int ttlda_transpose_pad_f64(const double* src, int64_t rows, int64_t cols, double* dst, int64_t dst_ld,
+                            void* stream); /* dst[c][r] = src[r][c]; dst is [cols][dst_ld], padding zeroed */
+int ttlda_transpose_unpad_f64(const double* src, int64_t rows, int64_t cols, int64_t src_ld, double* dst,
+                              void* stream); /* dst[c][r] = src[r][c]; src is [rows][src_ld], dst is [cols][rows] */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TTLDA_H */

@@ -1,0 +1,353 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (tuotuo_b200._native -> libttlda.so), against
+(a) the golden traces of the REAL reference (tests/golden/*.npz) and (b) the oracle on seeded inputs.
+
+Tolerances are north_star's: <= 1e-9 relative on gamma / lambda, <= 1e-8 on every perplexity; indices bit-exact.
+"""
+import json
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+import lda_oracle as orc
+from lda_oracle import CSRCorpus, OracleLDA
+
+pytestmark = pytest.mark.gpu
+
+TOL_STATE = 1e-9
+TOL_PERP = 1e-8
+
+
+def relerr(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) if a.size else 0.0
+
+
+def _load(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="module")
+def nv():
+    from tuotuo_b200 import _native
+
+    _native.load()
+    _native.check_device(0)
+    return _native
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def dpad(a, ld, dev):
+    """(rows, K) host array -> (rows, ld) device table with zero padding."""
+    t = torch.zeros((a.shape[0], ld), dtype=torch.float64, device=dev)
+    t[:, :a.shape[1]] = torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_dirichlet_expectation_known_answers(golden_dir, nv, dev):
+    g = _load(golden_dir, "psi_as103.npz")
+    for key_in, key_out in (("rows", "de_rows"), ("wide", "de_wide")):
+        a = g[key_in]
+        ld = nv.ld_for(a.shape[1])
+        t = dpad(a, ld, dev)
+        elog, ex = torch.empty_like(t), torch.empty_like(t)
+        nv.dirichlet_expectation(t, a.shape[1], elog, ex)
+        got = elog[:, :a.shape[1]].cpu().numpy()
+        # op-for-op AS-103: only FMA-contraction / libm last-bit differences are allowed
+        assert np.max(np.abs(got - g[key_out])) <= 1e-13 * max(1.0, np.max(np.abs(g[key_out])))
+        np.testing.assert_allclose(ex[:, :a.shape[1]].cpu().numpy(), np.exp(g[key_out]), rtol=1e-12)
+        assert float(ex[:, a.shape[1]:].abs().sum()) == 0.0
+    # long rows take the CTA-per-row kernel
+    rs = np.random.RandomState(3)
+    a = rs.gamma(1.0, 1.0, size=(3, 5003))
+    t = dpad(a, nv.ld_for(5003), dev)
+    elog = torch.empty_like(t)
+    nv.dirichlet_expectation(t, 5003, elog, None)
+    assert relerr(elog[:, :5003].cpu().numpy(), orc.dirichlet_expectation_2d(a)) < 1e-11
+    # 1-d in-place form
+    d1 = torch.as_tensor(g["d1_in"].copy()).to(dev)
+    out = torch.empty_like(d1)
+    nv.dirichlet_expectation_1d(d1, float(g["d1_prior"]), out)
+    np.testing.assert_allclose(d1.cpu().numpy(), g["d1_after"], rtol=0, atol=0)
+    assert relerr(out.cpu().numpy(), g["d1_out"]) < 1e-13
+
+
+def test_cutils_shim(golden_dir):
+    from tuotuo.cutils import _dirichlet_expectation_1d, _dirichlet_expectation_2d
+
+    g = _load(golden_dir, "psi_as103.npz")
+    assert relerr(_dirichlet_expectation_2d(g["wide"]), g["de_wide"]) < 1e-12
+    out32 = _dirichlet_expectation_2d(g["wide"].astype(np.float32))
+    assert out32.dtype == np.float32 and np.max(np.abs(out32 - g["de_wide32"])) < 2e-5
+    with pytest.raises(TypeError):
+        _dirichlet_expectation_2d(np.ones((2, 2), dtype=np.int64))
+    d1, out = g["d1_in"].copy(), np.empty_like(g["d1_in"])
+    _dirichlet_expectation_1d(d1, float(g["d1_prior"]), out)
+    np.testing.assert_array_equal(d1, g["d1_after"])
+    assert relerr(out, g["d1_out"]) < 1e-13
+
+
+def test_psi_exact_matches_scipy(nv, dev):
+    from scipy.special import psi
+
+    x = np.concatenate([np.logspace(-6, 6, 4001), np.linspace(0.5, 12, 2001)])
+    t = torch.as_tensor(x).to(dev)
+    out = torch.empty_like(t)
+    nv.psi_exact(t, out)
+    ref = psi(x)
+    assert np.max(np.abs(out.cpu().numpy() - ref) / np.maximum(1.0, np.abs(ref))) < 5e-15
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_bow_to_csr_and_csc_bit_exact(golden_dir, nv, dev):
+    from tuotuo_b200.corpus import DeviceCorpus
+
+    rs = np.random.RandomState(5)
+    V, D = 173, 211
+    lens = rs.poisson(30, size=D)
+    lens[[0, 7, 8, D - 1]] = 0  # empty documents, including first and last
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    tok = (rs.zipf(1.3, size=int(offs[-1])) % V).astype(np.int32)
+    ref = CSRCorpus.from_token_ids(tok, offs, V)
+    c = DeviceCorpus.from_token_ids(torch.as_tensor(tok).to(dev), torch.as_tensor(offs).to(dev), V)
+    rp, ci, ct = c.host_csr()
+    np.testing.assert_array_equal(rp, ref.rowptr)
+    np.testing.assert_array_equal(ci, ref.colidx)
+    np.testing.assert_array_equal(ct, ref.counts)
+    assert c.tokens == int(offs[-1]) and c.nnz == ref.nnz
+    # CSC mirror == scipy's transpose, documents ascending inside every word
+    import scipy.sparse as sp
+
+    m = sp.csr_matrix((ref.counts, ref.colidx, ref.rowptr), shape=(D, V)).tocsc()
+    m.sort_indices()
+    np.testing.assert_array_equal(c.colptr.cpu().numpy(), m.indptr)
+    np.testing.assert_array_equal(c.docidx.cpu().numpy()[:c.nnz], m.indices)
+    np.testing.assert_array_equal(c.ccounts.cpu().numpy()[:c.nnz], m.data)
+    # golden: the reference's Document on the README corpus
+    j = json.load(open(os.path.join(golden_dir, "cfg1_docs.json")))
+    from tuotuo.document import Document
+
+    d = Document({int(k): v for k, v in j["docs"].items()})
+    g = _load(golden_dir, "fit_cfg1.npz")
+    np.testing.assert_array_equal(d.doc_vocab_count_array, g["X"])
+    assert not d.doc_vocab_count_array.flags["C_CONTIGUOUS"] and d.doc_vocab_count_array.dtype == np.float64
+    # empty corpus
+    e = DeviceCorpus.from_token_ids(torch.zeros(0, dtype=torch.int32, device=dev),
+                                    torch.zeros(4, dtype=torch.int64, device=dev), 9)
+    assert e.nnz == 0 and e.rowptr.cpu().tolist() == [0, 0, 0, 0] and e.colptr.cpu().tolist() == [0] * 10
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode):
+    """theta/beta refresh -> estep -> sstats -> mstep -> tokens, all through the C ABI; returns host results."""
+    from tuotuo_b200.corpus import DeviceCorpus
+
+    c = DeviceCorpus.from_host_csr(X.rowptr, X.colidx, X.counts, X.V, dev)
+    ld = nv.ld_for(K)
+    D, V = X.D, X.V
+    gamma = dpad(gamma0, ld, dev)
+    lam = torch.zeros((V, ld), dtype=torch.float64, device=dev)
+    nv.transpose_pad(torch.as_tensor(np.ascontiguousarray(lam0)).to(dev), lam)
+    eT0 = torch.zeros((D, ld), dtype=torch.float64, device=dev)
+    eT1 = torch.zeros_like(eT0)
+    eB = torch.zeros_like(lam)
+    S = torch.zeros_like(lam)
+    lam_new = torch.zeros_like(lam)
+    colsum = torch.zeros(ld, dtype=torch.float64, device=dev)
+    part = torch.zeros((5, nv.NPART), dtype=torch.float64, device=dev)
+    iters = torch.zeros(2, dtype=torch.int64, device=dev)
+    ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+    ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
+    ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, V, ld), dtype=torch.uint8, device=dev)
+    av = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64).reshape(-1), (K,)))).to(dev)
+    asum = float(np.sum(alpha))
+    nv.theta_refresh(gamma, K, av, asum, eT0, part[0], ws)
+    nv.beta_refresh(lam, K, 1.0, eB, None, colsum, part[1], ws_m)
+    nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, eT0, eB, part[2], ws)
+    elbo0 = float(part[0, 0] + part[1, 0] + part[2, 0])
+    if mode == "atomic":
+        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, eT1, S, 100, 1e-5, iters, part[3], ws)
+    else:
+        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, eT1, None, 100, 1e-5, iters, part[3], ws)
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, eT0, eB, S, ws_s)
+    upd = torch.empty((K, V), dtype=torch.float64, device=dev)
+    nv.transpose_unpad(S * eB, K, upd)
+    elog_b = torch.zeros_like(lam)
+    nv.mstep(S, K, 1.0, eB, lam_new, elog_b, colsum, part[1], ws_m)
+    nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, eT1, eB, part[2], ws)
+    elbo1 = float(part[3, 1] + part[1, 0] + part[2, 0])
+    lam_out = torch.empty((K, V), dtype=torch.float64, device=dev)
+    nv.transpose_unpad(lam_new, K, lam_out)
+    eb_out = torch.empty((K, V), dtype=torch.float64, device=dev)
+    nv.transpose_unpad(elog_b, K, eb_out)
+    return dict(elbo0=elbo0, elbo1=elbo1, gamma=gamma[:, :K].cpu().numpy(), sstats=upd.cpu().numpy(),
+                lam=lam_out.cpu().numpy(), elogbeta=eb_out.cpu().numpy(), eT1=eT1[:, :K].cpu().numpy(),
+                iters=iters.cpu().numpy(), tok_in=float(part[3, 0]), count=float(part[3, 2]), pad=float(
+                    gamma[:, K:].abs().sum() + eT1[:, K:].abs().sum() + lam_new[:, K:].abs().sum() + eB[:, K:].abs().sum()))
+
+
+@pytest.mark.parametrize("mode", ["csc", "atomic"])
+def test_single_em_step_vs_reference(golden_dir, nv, dev, mode):
+    g = _load(golden_dir, "estep_small.npz")
+    X = CSRCorpus(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
+    r = _single_step(nv, dev, X, int(g["K"]), g["gamma0"], g["lam0"], 1, mode)
+    assert relerr(r["elbo0"], g["elbo0"]) < 1e-12
+    assert relerr(r["gamma"], g["gamma1"]) < TOL_STATE
+    assert relerr(r["sstats"], g["sstats1"]) < TOL_STATE
+    assert relerr(r["lam"], g["lam1"]) < TOL_STATE
+    assert np.max(np.abs(r["elogbeta"] - g["Elogbeta1"])) < 1e-11
+    assert relerr(r["eT1"], np.exp(g["Elogtheta1"])) < 1e-11
+    assert relerr(r["elbo1"], g["elbo1"]) < 1e-12
+    assert r["iters"][0] == 2 * X.D and r["iters"][1] == 0  # the reference's loop: exactly two passes per document
+    assert r["count"] == X.tokens and r["pad"] == 0.0
+
+
+FITS = ["fit_small.npz", "fit_nonexch.npz", "fit_sampling.npz", "fit_early.npz", "fit_ragged.npz", "fit_cfg2_slice.npz"]
+
+
+@pytest.mark.parametrize("name", FITS)
+def test_fit_traces_vs_reference(golden_dir, name):
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    g = _load(golden_dir, name)
+    kw = json.loads(str(g["kw"]))
+    exch = g["alpha0"].ndim == 0
+    doc = Document.from_csr(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
+    m = LDASmoothed(int(g["K"]), exchangeable_prior=exch, verbose=False)
+    if "D_population" in g:
+        m.D_population = int(g["D_population"])
+    perps = m.fit(doc, return_perplexities=True, **kw)
+    assert len(perps) == len(g["perplexities"]) and all(isinstance(p, np.float64) for p in perps)
+    assert relerr(perps, g["perplexities"]) < TOL_PERP
+    assert m._gamma_.shape == g["gamma"].shape and m._lambda_.shape == g["lam"].shape
+    assert relerr(m._gamma_, g["gamma"]) < TOL_STATE
+    assert relerr(m._lambda_, g["lam"]) < TOL_STATE
+    assert relerr(m._alpha_, g["alpha"]) < 1e-10 and relerr(m._eta_, g["eta"]) < 1e-10
+
+
+def test_fit_readme_config(golden_dir, capsys):
+    """BASELINE.json configs[0]: doc_generator M=100 L=20 -> Document -> LDASmoothed(5).fit, 100 iterations + hyper."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    j = json.load(open(os.path.join(golden_dir, "cfg1_docs.json")))
+    g = _load(golden_dir, "fit_cfg1.npz")
+    lda = LDASmoothed(num_topics=5)
+    perps = lda.fit({int(k): v for k, v in j["docs"].items()}, sampling=False, verbose=True, return_perplexities=True)
+    out = capsys.readouterr().out
+    assert "Var Inf - Word Dirichlet prior, Lambda\n(5, 40)" in out and "Var Inf - Topic Dirichlet prior, Gamma\n(100, 5)" in out
+    assert f"Init perplexity = {perps[0]}" in out and f"End perplexity = {perps[-1]}" in out
+    assert len(perps) == 102
+    assert relerr(perps, g["perplexities"]) < TOL_PERP
+    assert relerr(lda._gamma_, g["gamma"]) < TOL_STATE and relerr(lda._lambda_, g["lam"]) < TOL_STATE
+    assert relerr(lda._alpha_, g["alpha"]) < 1e-9 and relerr(lda._eta_, g["eta"]) < 1e-9
+    assert lda.M == 100 and lda.V == 40 and lda.train_doc.idx_to_vocab[0] == list(j["vocab_to_idx"])[0]
+    lda.get_top_k_words(3)
+    assert "Topic 4" in capsys.readouterr().out
+    assert lda.fit(lda.train_doc, em_num_step=1) is None  # return_perplexities defaults to False
+
+
+@pytest.mark.parametrize("K,V,D,L", [(100, 2000, 300, 120), (500, 1500, 64, 200), (1000, 1200, 40, 150),
+                                      (37, 700, 500, 60), (64, 500, 200, 50), (130, 900, 100, 80), (257, 600, 50, 90)])
+def test_fit_vs_oracle_many_K(K, V, D, L):
+    """Seeded corpora at topic counts covering every register-tiling variant (KP = 1..16), vs the C oracle."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(100 + K, D, V, min(K, 40), L, ragged=True)
+    X = CSRCorpus(rp, ci, ct, V)
+    o = OracleLDA(K, engine="c")
+    po = o.fit(X, em_num_step=3)
+    m = LDASmoothed(K, verbose=False)
+    pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert relerr(pg, po) < TOL_PERP
+    assert relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+    assert relerr(m._alpha_, o.alpha) < 1e-9 and relerr(m._eta_, o.eta) < 1e-9
+
+
+def test_atomic_mode_matches_csc_mode():
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(9, 400, 800, 20, 70, ragged=True)
+    doc = Document.from_csr(rp, ci, ct, 800)
+    a = LDASmoothed(24, verbose=False, sstats_mode="atomic")
+    pa = a.fit(doc, em_num_step=4, return_perplexities=True)
+    b = LDASmoothed(24, verbose=False, sstats_mode="csc")
+    pb = b.fit(doc, em_num_step=4, return_perplexities=True)
+    assert relerr(pa, pb) < 1e-12 and relerr(a._lambda_, b._lambda_) < 1e-11 and relerr(a._gamma_, b._gamma_) < 1e-11
+    # the two-pass path is bit-reproducible run to run
+    c = LDASmoothed(24, verbose=False, sstats_mode="csc")
+    pc = c.fit(doc, em_num_step=4, return_perplexities=True)
+    assert pb == pc and np.array_equal(b._lambda_, c._lambda_) and np.array_equal(b._gamma_, c._gamma_)
+
+
+def test_reference_shaped_step_api(golden_dir):
+    """e_step / m_step / em_step / approx_elbo / approx_perplexity keep the reference's argument and return shapes."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    g = _load(golden_dir, "estep_small.npz")
+    X = CSRCorpus(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
+    doc = Document.from_csr(X.rowptr, X.colidx, X.counts, X.V)
+    m = LDASmoothed(int(g["K"]), verbose=False)
+    m.fit(doc, em_num_step=0, update_hyper_parms=False)
+    Xd = doc.doc_vocab_count_array
+    elbo0, (Et0, Eb0) = m.approx_elbo(Xd)
+    assert relerr(elbo0, g["elbo0"]) < 1e-12 and Et0.shape == (X.D, m.K) and Eb0.shape == (m.K, X.V)
+    assert np.max(np.abs(Et0 - g["Elogtheta0"])) < 1e-11 and np.max(np.abs(Eb0 - g["Elogbeta0"])) < 1e-11
+    gam, (S, Et1) = m.e_step(Xd, Et0, Eb0)
+    assert relerr(gam, g["gamma1"]) < TOL_STATE and relerr(S, g["sstats1"]) < TOL_STATE
+    assert np.max(np.abs(Et1 - g["Elogtheta1"])) < 1e-11
+    lam, Eb1 = m.m_step(S)
+    assert relerr(lam, g["lam1"]) < TOL_STATE and np.max(np.abs(Eb1 - g["Elogbeta1"])) < 1e-11
+    perp, _ = m.approx_perplexity(Xd, False, Et1, Eb1)
+    assert relerr(perp, np.exp(-g["elbo1"] / X.tokens)) < TOL_PERP
+
+
+def test_estep_iteration_cap_statistics(golden_dir, nv, dev):
+    """max_iter = 0 reproduces the reference's `it > step` warning condition for every document."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    g = _load(golden_dir, "estep_small.npz")
+    doc = Document.from_csr(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
+    m = LDASmoothed(int(g["K"]), verbose=False)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.fit(doc, em_num_step=1, e_num_step=0, update_hyper_parms=False)
+    assert any("Maximum iteration reached" in str(x.message) for x in w)
+    assert relerr(m._gamma_, g["gamma1"]) < TOL_STATE
+
+
+def test_invariants_at_scale(nv, dev):
+    """Size-independent properties on a corpus far beyond what the oracle can check (200k docs x 300 tokens, K=100):
+    sum_k (gamma_dk - alpha) = document length; sum_wk sstats*eB = token count; perplexity decreases."""
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import synthetic_document
+
+    doc = synthetic_document("cfg3", device=dev, docs=200_000)
+    m = LDASmoothed(100, verbose=False)
+    perps = m.fit(doc, em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    st = m._st
+    c = st.corpus
+    assert c.tokens == 200_000 * 300
+    lens = torch.zeros(c.D, dtype=torch.float64, device=dev)
+    rows = torch.repeat_interleave(torch.arange(c.D, device=dev), torch.diff(c.rowptr))
+    lens.index_add_(0, rows, c.counts.to(torch.float64))
+    assert float(((st.gamma[:, :100].sum(1) - 100.0) - lens).abs().max()) < 1e-9
+    tot = float((st.lam[:, :100] - 1.0).sum())  # lambda - eta = sstats * eB
+    assert abs(tot - c.tokens) / c.tokens < 1e-12
+    assert perps[0] > perps[1] > perps[2] > perps[3]
+    assert st.terms["count"] == c.tokens

@@ -1,0 +1,125 @@
+"""Host-side logic that needs no GPU: text pipeline, vocabulary ids, Document API surface, sharding, generator."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tuotuo_b200.corpus import balanced_doc_partition
+from tuotuo_b200.document import Document
+from tuotuo_b200.text import STOPWORDS, text_pipeline
+
+
+def test_vocab_ids_bit_exact_vs_reference_cfg1(golden_dir, capsys):
+    j = json.load(open(os.path.join(golden_dir, "cfg1_docs.json")))
+    docs = {int(k): v for k, v in j["docs"].items()}
+    d = Document(docs)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == "There are 100 documents in the dataset after processing"
+    assert out[1] == "On average estimated document length is 20.0 words per document after processing"
+    assert out[2] == "There are 40 unique vocab in the corpus after processing"
+    assert d.vocab_to_idx == j["vocab_to_idx"] and list(d.vocab_to_idx) == list(j["vocab_to_idx"])
+    assert d.sample_docs_list == j["sample_docs_list"]
+    assert d.M == 100 and d.V == 40 and d.num_doc_population == 100
+    assert d.idx_to_vocab[0] == list(j["vocab_to_idx"])[0]
+    g = np.load(os.path.join(golden_dir, "fit_cfg1.npz"))
+    # token stream -> per-document sorted unique counts must equal the reference's dense matrix rows
+    for i in (0, 17, 99):
+        ids = d._token_ids[d._doc_offsets[i]:d._doc_offsets[i + 1]]
+        u, c = np.unique(ids, return_counts=True)
+        np.testing.assert_array_equal(u, g["colidx"][g["rowptr"][i]:g["rowptr"][i + 1]])
+        np.testing.assert_array_equal(c, g["counts"][g["rowptr"][i]:g["rowptr"][i + 1]])
+
+
+def test_text_pipeline_vs_reference_free_text(golden_dir):
+    """Accents, punctuation, case-sensitivity, stop words ('not' is kept), empty document -> ''."""
+    j = json.load(open(os.path.join(golden_dir, "document_vocab.json")))
+    d = Document(dict(j["texts"]))
+    assert d.sample_docs_list == j["sample_docs_list"]
+    assert d.vocab_to_idx == j["vocab_to_idx"] and list(d.vocab_to_idx) == list(j["vocab_to_idx"])
+    assert d.M == j["M"] and d.V == j["V"] and d.num_doc_population == j["num_doc_population"]
+    assert "" in d.vocab_to_idx  # the empty document contributes the token ''
+    assert "not" not in STOPWORDS and "the" in STOPWORDS
+    assert text_pipeline("  The   fox!!  ") == "fox"
+
+
+def test_num_doc_population():
+    d = Document({0: "a b", 1: "b c"}, num_doc_population=1000)
+    assert d.num_doc_population == 1000
+
+
+def test_from_dense_and_shard_roundtrip():
+    rs = np.random.RandomState(0)
+    X = rs.poisson(0.3, size=(37, 23)).astype(float)
+    X[5] = 0
+    d = Document.from_dense(X)
+    rp, ci, ct = d._host_csr
+    assert d.M == 37 and d.V == 23 and rp[-1] == np.count_nonzero(X)
+    np.testing.assert_array_equal(d.doc_vocab_count_array, X)
+    assert d.doc_vocab_count_df.shape == (37, 23)
+    assert d.vocab_doc_count_dict["w3"] == [int(v) for v in X[:, 3]]
+    parts = [d.shard(r, 3) for r in range(3)]
+    assert sum(p.M for p in parts) == 37
+    np.testing.assert_array_equal(np.vstack([p.doc_vocab_count_array for p in parts]), X)
+    assert parts[0].doc_range[0] == 0 and parts[-1].doc_range[1] == 37
+    with pytest.raises(ValueError):
+        Document.from_dense(X + 0.5)
+
+
+def test_balanced_partition_properties():
+    rs = np.random.RandomState(1)
+    lens = rs.poisson(50, size=1000)
+    lens[::7] = 0
+    rowptr = np.concatenate([[0], np.cumsum(lens)])
+    for world in (1, 2, 4, 8):
+        b = balanced_doc_partition(rowptr, world)
+        assert b[0] == 0 and b[-1] == 1000 and np.all(np.diff(b) >= 0) and len(b) == world + 1
+        loads = np.diff(rowptr[b])
+        assert loads.max() - loads.min() <= 2 * lens.max()
+    b = balanced_doc_partition(np.array([0, 0, 0, 0]), 2)  # all-empty corpus
+    assert b[0] == 0 and b[-1] == 3
+
+
+def test_shard_token_stream():
+    ids = np.arange(30, dtype=np.int32) % 7
+    offs = np.array([0, 5, 5, 12, 20, 30], dtype=np.int64)
+    d = Document.from_token_ids(ids, offs, 7)
+    p0, p1 = d.shard(0, 2), d.shard(1, 2)
+    assert p0.M + p1.M == 5
+    np.testing.assert_array_equal(np.concatenate([p0._token_ids, p1._token_ids]), ids)
+    assert p0._doc_offsets[0] == 0 and p1._doc_offsets[0] == 0
+
+
+def test_doc_generator_api():
+    import torch
+
+    from tuotuo.generator import doc_generator
+
+    torch.manual_seed(3)
+    g = doc_generator(M=7, L=11, topic_prior=torch.tensor([1, 1, 1, 1, 1], dtype=torch.double))
+    assert g.K == 5 and g.V == 40 and g.M == 7 and g.L == 11
+    assert g.beta.shape == (5, 40) and g.beta.dtype == torch.double
+    assert torch.allclose(g.beta.sum(1), torch.ones(5, dtype=torch.double))
+    assert g.theta.shape == (7, 5)
+    assert g.words[13]["name"] == "Olympic" and g.topics[4] == "law" and g.words[0]["prob"][0] == 0.96
+    docs = g.generate_doc()
+    assert list(docs) == list(range(7)) and all(len(v.split(" ")) == 11 for v in docs.values())
+    assert docs is g.docs
+    names = {w["name"] for w in g.words.values()}
+    assert all(t in names for v in docs.values() for t in v.split(" "))
+    with pytest.raises(AssertionError):
+        doc_generator(M=1, L=1, topic_prior=torch.ones(4, dtype=torch.double))
+
+
+def test_lda_constructor_prints_and_priors(capsys):
+    from tuotuo.lda_model import LDASmoothed
+
+    m = LDASmoothed(num_topics=5)
+    out = capsys.readouterr().out
+    assert "Topic Dirichlet Prior, α\n1\n" in out and "Exchangeable Word Dirichlet Prior, Eta \n1\n" in out
+    assert m._alpha_ == 1 and m._eta_ == 1 and m.K == 5
+    m2 = LDASmoothed(num_topics=6, exchangeable_prior=False, verbose=False)
+    np.random.seed(42)
+    np.testing.assert_array_equal(m2._alpha_, np.random.gamma(shape=100, scale=0.01, size=(1, 6)))
+    with pytest.raises(AttributeError):
+        m._lambda_

@@ -1,0 +1,253 @@
+"""ctypes binding of ``libttlda.so`` (C ABI declared in ``include/ttlda.h``).
+
+There is no CPU fallback: if the library is missing or a call fails, this module raises.  torch is used only
+for device memory and streams — every function takes ``torch.Tensor`` arguments, checks device/dtype/contiguity
+and passes ``data_ptr()`` plus the current CUDA stream to the C entry point.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libttlda.so")
+
+NPART = 8
+MAX_K = 1024
+
+_i64 = ctypes.c_int64
+_f64 = ctypes.c_double
+_ptr = ctypes.c_void_p
+
+# name -> (restype, argtypes)   — mirrors include/ttlda.h one to one
+SIGNATURES = {
+    "ttlda_version": (ctypes.c_int, []),
+    "ttlda_last_error": (ctypes.c_char_p, []),
+    "ttlda_check_device": (ctypes.c_int, [ctypes.c_int]),
+    "ttlda_ld_for": (_i64, [_i64]),
+    "ttlda_dirichlet_expectation_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
+    "ttlda_dirichlet_expectation_1d_f64": (ctypes.c_int, [_ptr, _f64, _ptr, _i64, _ptr]),
+    "ttlda_bow_to_csr_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ttlda_bow_to_csr": (ctypes.c_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_csr_to_csc_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ttlda_csr_to_csc": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_reduce_workspace_bytes": (_i64, []),
+    "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
+                                       _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64]),
+    "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
+                                            _ptr]),
+    "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
+    "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
+                                              _ptr]),
+    "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_hyper_stats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_psi_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
+    "ttlda_transpose_pad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr]),
+    "ttlda_transpose_unpad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
+}
+
+
+class TTLDAError(RuntimeError):
+    pass
+
+
+_lib = None
+launch_count = 0  # C-ABI calls made so far
+kernel_count = 0  # kernels of libttlda launched so far (bench.py reports the per-region delta as gpu_launches)
+timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ...] on the current stream
+
+# hand-written kernels launched by each entry point (CUB sort/RLE passes and memsets are not counted)
+KERNELS_PER_CALL = {
+    "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
+    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2,
+    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_sstats_csc_f64": 2, "ttlda_mstep_f64": 4,
+    "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
+    "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
+}
+
+
+def load():
+    """Load libttlda.so (no fallback).  Safe without a GPU: only binds symbols."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TTLDAError(
+            f"{LIB_PATH} not found: build it with `python -m tuotuo_b200.build` — there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, name: str):
+    if rc != 0:
+        msg = load().ttlda_last_error().decode("utf-8", "replace")
+        raise TTLDAError(f"{name} failed ({rc}): {msg}")
+
+
+def _p(t: torch.Tensor | None, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise TTLDAError("libttlda takes CUDA tensors only (no CPU fallback)")
+    if not t.is_contiguous():
+        raise TTLDAError("tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TTLDAError(f"expected dtype {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _call(name, *args):
+    global launch_count, kernel_count
+    launch_count += 1
+    kernel_count += KERNELS_PER_CALL[name]
+    fn = getattr(load(), name)
+    if timing is None:
+        _check(fn(*args), name)
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    timing.setdefault(name, []).append((e0, e1))
+    _check(rc, name)
+
+
+def ld_for(K: int) -> int:
+    return (int(K) + 3) // 4 * 4
+
+
+def version() -> int:
+    return int(load().ttlda_version())
+
+
+def check_device(device: int = 0) -> None:
+    _check(load().ttlda_check_device(int(device)), "ttlda_check_device")
+
+
+f64, i64, i32 = torch.float64, torch.int64, torch.int32
+
+
+# ---- thin wrappers ------------------------------------------------------------------------------------------------
+def reduce_workspace_bytes() -> int:
+    return int(load().ttlda_reduce_workspace_bytes())
+
+
+def dirichlet_expectation(a, cols, out_elog=None, out_exp=None):
+    rows, ld = a.shape
+    _call("ttlda_dirichlet_expectation_f64", _p(a, f64), rows, int(cols), ld, _p(out_elog, f64), _p(out_exp, f64),
+          _stream())
+
+
+def dirichlet_expectation_1d(doc_topic, prior, out):
+    _call("ttlda_dirichlet_expectation_1d_f64", _p(doc_topic, f64), float(prior), _p(out, f64), doc_topic.numel(),
+          _stream())
+
+
+def bow_to_csr_workspace_bytes(T, D, V) -> int:
+    r = int(load().ttlda_bow_to_csr_workspace_bytes(int(T), int(D), int(V)))
+    if r < 0:
+        _check(r, "ttlda_bow_to_csr_workspace_bytes")
+    return r
+
+
+def bow_to_csr(token_ids, doc_offsets, V, rowptr, colidx, counts, nnz_out, ws):
+    T, D = token_ids.numel(), doc_offsets.numel() - 1
+    _call("ttlda_bow_to_csr", _p(token_ids, i32), _p(doc_offsets, i64), T, D, int(V), _p(rowptr, i64),
+          _p(colidx, i32), _p(counts, i32), _p(nnz_out, i64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def csr_to_csc_workspace_bytes(nnz, D, V) -> int:
+    r = int(load().ttlda_csr_to_csc_workspace_bytes(int(nnz), int(D), int(V)))
+    if r < 0:
+        _check(r, "ttlda_csr_to_csc_workspace_bytes")
+    return r
+
+
+def csr_to_csc(rowptr, colidx, counts, D, V, nnz, colptr, docidx, ccounts, ws):
+    _call("ttlda_csr_to_csc", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), int(D), int(V), int(nnz),
+          _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def theta_refresh(gamma, K, alpha_vec, alpha_sum, eT, partial, ws):
+    D, ld = gamma.shape
+    _call("ttlda_theta_refresh_f64", _p(gamma, f64), D, int(K), ld, _p(alpha_vec, f64), float(alpha_sum), _p(eT, f64),
+          _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma, eT_out, sstats_atomic, max_iter, tol,
+          iters, partial, ws):
+    D, ld = gamma.shape
+    _call("ttlda_estep_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
+          _p(alpha_vec, f64), float(alpha_sum), _p(eT_in, f64), _p(eB, f64), _p(gamma, f64), _p(eT_out, f64),
+          _p(sstats_atomic, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
+          ws.numel() * ws.element_size(), _stream())
+
+
+def sstats_workspace_bytes(nnz, V, ld) -> int:
+    return int(load().ttlda_sstats_workspace_bytes(int(nnz), int(V), int(ld)))
+
+
+def sstats_csc(colptr, docidx, ccounts, V, K, nnz, eT, eB, sstats, ws):
+    ld = eB.shape[1]
+    _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), int(V), int(K), ld, int(nnz),
+          _p(eT, f64), _p(eB, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def mstep_workspace_bytes(V, ld) -> int:
+    return int(load().ttlda_mstep_workspace_bytes(int(V), int(ld)))
+
+
+def mstep(sstats, K, eta, eB, lam, elogbeta, colsum, partial, ws):
+    V, ld = sstats.shape
+    _call("ttlda_mstep_f64", _p(sstats, f64), V, int(K), ld, float(eta), _p(eB, f64), _p(lam, f64), _p(elogbeta, f64),
+          _p(colsum, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def beta_refresh(lam, K, eta, eB, elogbeta, colsum, partial, ws):
+    V, ld = lam.shape
+    _call("ttlda_beta_refresh_f64", _p(lam, f64), V, int(K), ld, float(eta), _p(eB, f64), _p(elogbeta, f64),
+          _p(colsum, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def elbo_tokens(rowptr, colidx, counts, K, eT, eB, partial, ws):
+    D, ld = eT.shape
+    _call("ttlda_elbo_tokens_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), ld, _p(eT, f64),
+          _p(eB, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def hyper_stats(x, cols, partial, ws):
+    rows, ld = x.shape
+    _call("ttlda_hyper_stats_f64", _p(x, f64), rows, int(cols), ld, _p(partial, f64), _p(ws),
+          ws.numel() * ws.element_size(), _stream())
+
+
+def psi_exact(x, out):
+    _call("ttlda_psi_f64", _p(x, f64), x.numel(), _p(out, f64), _stream())
+
+
+def transpose_pad(src, dst):
+    """dst[c, r] = src[r, c];  src (rows, cols) contiguous, dst (cols, dst_ld>=rows), padding zeroed."""
+    rows, cols = src.shape
+    assert dst.shape[0] == cols
+    _call("ttlda_transpose_pad_f64", _p(src, f64), rows, cols, _p(dst, f64), dst.shape[1], _stream())
+
+
+def transpose_unpad(src, cols, dst):
+    """dst[c, r] = src[r, c] for c < cols;  src (rows, src_ld), dst (cols, rows)."""
+    rows, src_ld = src.shape
+    assert dst.shape == (cols, rows)
+    _call("ttlda_transpose_unpad_f64", _p(src, f64), rows, int(cols), src_ld, _p(dst, f64), _stream())

@@ -1,0 +1,96 @@
+"""Device-resident doc-term matrix: CSR (document-major) plus its CSC mirror (word-major).
+
+Replaces the dense ``Document.doc_vocab_count_array`` (tuotuo/document.py:33-36, built by tuotuo/utils.py:177-206):
+an M x V float64 matrix cannot exist at the target sizes (400 GB at 1M docs x 50k words).  The E-step reads the CSR
+rows — exactly ``np.nonzero(X[d,:])`` / ``X[d, ids]`` of tuotuo/lda_model.py:226-227 — and the M-step statistics
+are accumulated from the CSC side.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as nv
+
+
+class DeviceCorpus:
+    """rowptr int64[D+1], colidx int32[nnz] (ascending per row), counts int32[nnz] and the CSC mirror, on one device."""
+
+    def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = True):
+        assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and counts.dtype == torch.int32
+        self.rowptr, self.colidx, self.counts = rowptr.contiguous(), colidx.contiguous(), counts.contiguous()
+        self.device = rowptr.device
+        self.D = int(rowptr.numel() - 1)
+        self.V = int(V)
+        self.nnz = int(colidx.numel())
+        self.tokens = int(counts.sum(dtype=torch.int64).item()) if self.nnz else 0
+        self.colptr = self.docidx = self.ccounts = None
+        if build_csc:
+            self.build_csc()
+
+    # -- constructors ----------------------------------------------------------------------------------------------
+    @staticmethod
+    def from_host_csr(rowptr: np.ndarray, colidx: np.ndarray, counts: np.ndarray, V: int, device, **kw):
+        dev = torch.device(device)
+        return DeviceCorpus(torch.as_tensor(np.ascontiguousarray(rowptr, dtype=np.int64)).to(dev),
+                            torch.as_tensor(np.ascontiguousarray(colidx, dtype=np.int32)).to(dev),
+                            torch.as_tensor(np.ascontiguousarray(counts, dtype=np.int32)).to(dev), V, **kw)
+
+    @staticmethod
+    def from_token_ids(token_ids: torch.Tensor, doc_offsets: torch.Tensor, V: int, **kw):
+        """Token-id stream (int32, device) + document offsets (int64[D+1], device) -> CSR via ttlda_bow_to_csr."""
+        dev = token_ids.device
+        T, D = token_ids.numel(), doc_offsets.numel() - 1
+        ws = torch.empty(nv.bow_to_csr_workspace_bytes(T, D, V), dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(D + 1, dtype=torch.int64, device=dev)
+        colidx = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+        counts = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
+        nnz_out = torch.zeros(1, dtype=torch.int64, device=dev)
+        nv.bow_to_csr(token_ids.contiguous(), doc_offsets.contiguous(), V, rowptr, colidx, counts, nnz_out, ws)
+        nnz = int(nnz_out.item())
+        del ws
+        return DeviceCorpus(rowptr, colidx[:nnz].clone(), counts[:nnz].clone(), V, **kw)
+
+    def build_csc(self):
+        dev = self.device
+        ws = torch.empty(nv.csr_to_csc_workspace_bytes(self.nnz, self.D, self.V), dtype=torch.uint8, device=dev)
+        self.colptr = torch.empty(self.V + 1, dtype=torch.int64, device=dev)
+        self.docidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, self.colptr, self.docidx,
+                      self.ccounts, ws)
+        del ws
+
+    # -- host views ----------------------------------------------------------------------------------------------------
+    def host_csr(self):
+        return (self.rowptr.cpu().numpy(), self.colidx.cpu().numpy(), self.counts.cpu().numpy())
+
+    def to_dense(self) -> np.ndarray:
+        """M x V float64 (the reference's doc_vocab_count_array).  Small corpora only."""
+        if self.D * self.V > 2 ** 31:
+            raise MemoryError(f"dense {self.D} x {self.V} count matrix requested; use the CSR arrays instead")
+        rp, ci, ct = self.host_csr()
+        X = np.zeros((self.D, self.V), dtype=np.float64)
+        rows = np.repeat(np.arange(self.D), np.diff(rp))
+        X[rows, ci] = ct
+        return X
+
+    def nbytes(self) -> int:
+        n = self.rowptr.numel() * 8 + self.nnz * 8
+        if self.colptr is not None:
+            n += self.colptr.numel() * 8 + self.nnz * 8
+        return n
+
+
+def balanced_doc_partition(rowptr: np.ndarray, world: int) -> np.ndarray:
+    """Contiguous, nnz-balanced document blocks: returns int64[world+1] document boundaries.
+
+    Multi-GPU sharding of SURVEY.md §8(e): documents are independent given lambda, so rank r owns documents
+    [b[r], b[r+1]) and the matching gamma rows; only the K x V statistics cross NVLink."""
+    rowptr = np.asarray(rowptr, dtype=np.int64)
+    D = len(rowptr) - 1
+    nnz = int(rowptr[-1])
+    targets = (np.arange(1, world, dtype=np.float64) * nnz / world)
+    cuts = np.searchsorted(rowptr, targets, side="left").astype(np.int64)
+    b = np.concatenate([[0], np.clip(cuts, 0, D), [D]]).astype(np.int64)
+    return np.maximum.accumulate(b)

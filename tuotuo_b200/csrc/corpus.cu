@@ -1,0 +1,231 @@
+// corpus.cu — bag-of-words construction on the device: token-id stream -> CSR doc-term matrix, and its CSC mirror.
+//
+// Reference: get_vocab_from_docs / get_np_wct (tuotuo/utils.py:177-206) build a dense V x M float64 count matrix
+// with Python dict/list loops; Document exposes its transpose (tuotuo/document.py:33-36) and the E-step reads rows
+// through np.nonzero(X[d,:]) (tuotuo/lda_model.py:226-227), i.e. ascending word ids with their counts.  The CSR
+// built here holds exactly those (ids, counts) per document; integer work, bit-exact.
+//
+// Sorting/scan plumbing uses CUB (ships with the CUDA toolkit); key packing, run splitting and pointer
+// construction are hand-written.  One-time cost per corpus, outside the EM loop.
+#include <cub/cub.cuh>
+
+#include "ttlda_common.cuh"
+
+namespace ttlda {
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int bits_for(int64_t n)
+{
+    int b = 1;
+    while (((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+// key = (doc << vbits) | word for every token; doc found by binary search in doc_offsets.
+__global__ void pack_keys_kernel(const int32_t* __restrict__ tok, const int64_t* __restrict__ offs, int64_t T,
+                                 int64_t D, int vbits, uint64_t* __restrict__ keys)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < T; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = D;  // last d with offs[d] <= i
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (offs[mid] <= i) lo = mid; else hi = mid;
+        }
+        keys[i] = ((uint64_t)lo << vbits) | (uint64_t)(uint32_t)tok[i];
+    }
+}
+
+// unique (doc,word) keys -> colidx, and rowptr from the doc boundaries (documents may be empty).
+__global__ void split_runs_kernel(const uint64_t* __restrict__ ukeys, const int64_t* __restrict__ nruns_p, int64_t D,
+                                  int vbits, int32_t* __restrict__ colidx, int64_t* __restrict__ rowptr,
+                                  int64_t* __restrict__ nnz_out)
+{
+    const int64_t n = *nruns_p;
+    const uint64_t vmask = ((uint64_t)1 << vbits) - 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t dcur = (i < n) ? (int64_t)(ukeys[i] >> vbits) : D;
+        const int64_t dprev = (i > 0) ? (int64_t)(ukeys[i - 1] >> vbits) : -1;
+        if (i < n) colidx[i] = (int32_t)(ukeys[i] & vmask);
+        for (int64_t d = dprev + 1; d <= dcur; ++d) rowptr[d] = i;  // rowptr[D] = n when i == n
+        if (i == n) *nnz_out = n;
+    }
+}
+
+__global__ void iota_u32_kernel(uint32_t* __restrict__ v, int64_t n)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] = (uint32_t)i;
+}
+
+// after the stable sort by word: gather doc id (binary search in rowptr) and count of each CSR position; build colptr
+__global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ spos,
+                                  const int64_t* __restrict__ rowptr, const int32_t* __restrict__ counts, int64_t D,
+                                  int64_t V, int64_t nnz, int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
+                                  int32_t* __restrict__ ccounts)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t wcur = (i < nnz) ? (int64_t)skeys[i] : V;
+        const int64_t wprev = (i > 0) ? (int64_t)skeys[i - 1] : -1;
+        for (int64_t w = wprev + 1; w <= wcur; ++w) colptr[w] = i;
+        if (i < nnz) {
+            const int64_t p = spos[i];
+            int64_t lo = 0, hi = D;  // last d with rowptr[d] <= p  (skips empty documents correctly)
+            while (hi - lo > 1) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (rowptr[mid] <= p) lo = mid; else hi = mid;
+            }
+            docidx[i] = (int32_t)lo;
+            ccounts[i] = counts[p];
+        }
+    }
+}
+
+struct BowWs {
+    uint64_t *keys, *skeys, *ukeys;
+    int64_t* nruns;
+    void* cub;
+    size_t cub_bytes, total;
+};
+
+static cudaError_t bow_layout(int64_t T, int64_t D, int64_t V, char* base, BowWs& w)
+{
+    size_t sort_b = 0, rle_b = 0;
+    const int end_bit = bits_for(V) + bits_for(D);
+    cudaError_t e = cub::DeviceRadixSort::SortKeys(nullptr, sort_b, (uint64_t*)nullptr, (uint64_t*)nullptr, T, 0, end_bit);
+    if (e != cudaSuccess) return e;
+    e = cub::DeviceRunLengthEncode::Encode(nullptr, rle_b, (uint64_t*)nullptr, (uint64_t*)nullptr, (int32_t*)nullptr,
+                                           (int64_t*)nullptr, (int)T);
+    if (e != cudaSuccess) return e;
+    size_t off = 0;
+    w.keys = (uint64_t*)(base + off);  off += align256((size_t)T * 8);
+    w.skeys = (uint64_t*)(base + off); off += align256((size_t)T * 8);
+    w.ukeys = (uint64_t*)(base + off); off += align256((size_t)T * 8);
+    w.nruns = (int64_t*)(base + off);  off += 256;
+    w.cub = base + off;
+    w.cub_bytes = align256(sort_b > rle_b ? sort_b : rle_b);
+    off += w.cub_bytes;
+    w.total = off;
+    return cudaSuccess;
+}
+
+struct CscWs {
+    uint32_t *skeys, *pos, *spos;
+    void* cub;
+    size_t cub_bytes, total;
+};
+
+static cudaError_t csc_layout(int64_t nnz, int64_t V, char* base, CscWs& w)
+{
+    size_t sort_b = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                    (uint32_t*)nullptr, (uint32_t*)nullptr, nnz, 0, bits_for(V));
+    if (e != cudaSuccess) return e;
+    size_t off = 0;
+    w.skeys = (uint32_t*)(base + off); off += align256((size_t)nnz * 4);
+    w.pos = (uint32_t*)(base + off);   off += align256((size_t)nnz * 4);
+    w.spos = (uint32_t*)(base + off);  off += align256((size_t)nnz * 4);
+    w.cub = base + off;
+    w.cub_bytes = align256(sort_b);
+    off += w.cub_bytes;
+    w.total = off;
+    return cudaSuccess;
+}
+
+static int grid_1d(int64_t n)
+{
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)kSMs * 16) g = (int64_t)kSMs * 16;
+    return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace ttlda
+
+using namespace ttlda;
+
+extern "C" {
+
+int64_t ttlda_bow_to_csr_workspace_bytes(int64_t T, int64_t D, int64_t V)
+{
+    if (T < 0 || D < 0 || V < 0) return TTLDA_EINVAL;
+    BowWs w;
+    cudaError_t e = bow_layout(T, D, V, nullptr, w);
+    if (e != cudaSuccess) return cuda_fail(e, "bow_to_csr workspace query");
+    return (int64_t)w.total;
+}
+
+int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64_t T, int64_t D, int64_t V,
+                     int64_t* rowptr, int32_t* colidx, int32_t* counts, int64_t* nnz_out, void* workspace,
+                     int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(doc_offsets && rowptr && nnz_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(T == 0 || (token_ids && colidx && counts), "NULL pointer");
+    TTLDA_REQUIRE(T >= 0 && D >= 0 && V >= 0, "negative size");
+    TTLDA_REQUIRE(T < ((int64_t)1 << 31), "token stream per call must be < 2^31 (split the corpus)");
+    TTLDA_REQUIRE(bits_for(V) + bits_for(D) <= 64, "D*V key does not fit 64 bits");
+    cudaStream_t s = (cudaStream_t)stream;
+    BowWs w;
+    cudaError_t e = bow_layout(T, D, V, (char*)workspace, w);
+    if (e != cudaSuccess) return cuda_fail(e, "bow_to_csr layout");
+    if ((int64_t)w.total > workspace_bytes) {
+        set_error("bow_to_csr: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+        return TTLDA_EWORKSPACE;
+    }
+    const int vbits = bits_for(V);
+    if (T > 0) {
+        pack_keys_kernel<<<grid_1d(T), 256, 0, s>>>(token_ids, doc_offsets, T, D, vbits, w.keys);
+        TTLDA_LAUNCH_CHECK("pack_keys");
+        e = cub::DeviceRadixSort::SortKeys(w.cub, w.cub_bytes, w.keys, w.skeys, T, 0, vbits + bits_for(D), s);
+        if (e != cudaSuccess) return cuda_fail(e, "radix sort (bow)");
+        e = cub::DeviceRunLengthEncode::Encode(w.cub, w.cub_bytes, w.skeys, w.ukeys, counts, w.nruns, (int)T, s);
+        if (e != cudaSuccess) return cuda_fail(e, "run-length encode");
+    } else {
+        e = cudaMemsetAsync(w.nruns, 0, sizeof(int64_t), s);
+        if (e != cudaSuccess) return cuda_fail(e, "memset");
+    }
+    split_runs_kernel<<<grid_1d(T + 1), 256, 0, s>>>(w.ukeys, w.nruns, D, vbits, colidx, rowptr, nnz_out);
+    TTLDA_LAUNCH_CHECK("split_runs");
+    return TTLDA_OK;
+}
+
+int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V)
+{
+    (void)D;
+    if (nnz < 0 || V < 0) return TTLDA_EINVAL;
+    CscWs w;
+    cudaError_t e = csc_layout(nnz, V, nullptr, w);
+    if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc workspace query");
+    return (int64_t)w.total;
+}
+
+int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
+                     int64_t nnz, int64_t* colptr, int32_t* docidx, int32_t* ccounts, void* workspace,
+                     int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(rowptr && colptr && workspace, "NULL pointer");
+    TTLDA_REQUIRE(nnz == 0 || (colidx && counts && docidx && ccounts), "NULL pointer");
+    TTLDA_REQUIRE(nnz >= 0 && D >= 0 && V >= 0, "negative size");
+    TTLDA_REQUIRE(nnz < ((int64_t)1 << 32), "nnz per device must be < 2^32");
+    cudaStream_t s = (cudaStream_t)stream;
+    CscWs w;
+    cudaError_t e = csc_layout(nnz, V, (char*)workspace, w);
+    if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc layout");
+    if ((int64_t)w.total > workspace_bytes) {
+        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+        return TTLDA_EWORKSPACE;
+    }
+    if (nnz > 0) {
+        iota_u32_kernel<<<grid_1d(nnz), 256, 0, s>>>(w.pos, nnz);
+        TTLDA_LAUNCH_CHECK("iota");
+        // LSD radix sort is stable: within a word, CSR positions (hence documents) stay ascending.
+        e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, reinterpret_cast<const uint32_t*>(colidx), w.skeys,
+                                            w.pos, w.spos, nnz, 0, bits_for(V), s);
+        if (e != cudaSuccess) return cuda_fail(e, "radix sort (csc)");
+    }
+    csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, rowptr, counts, D, V, nnz, colptr, docidx,
+                                                       ccounts);
+    TTLDA_LAUNCH_CHECK("csc_gather");
+    return TTLDA_OK;
+}
+
+}  // extern "C"

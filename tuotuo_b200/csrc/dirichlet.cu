@@ -1,0 +1,244 @@
+// dirichlet.cu — row-wise Dirichlet expectation (AS-103 digamma), theta refresh + theta-prior ELBO term,
+// exact-digamma Newton statistics.
+//
+// Reference: tuotuo/cutils.pyx:11-93 (psi, _dirichlet_expectation_1d/_2d); call sites tuotuo/lda_model.py:116,
+// 120,256,281 ; expec_real_dist_minus_suro_dist tuotuo/lda_model.py:25-46 ; update_alpha/eta :449-462,:522-528.
+//
+// HBM-bound elementwise/row kernels: rows are read once with coalesced accesses, reductions are warp shuffles
+// (rows <= 2048 columns: one warp per row) or a CTA per row (long rows, e.g. a (K,V) matrix).
+#include "ttlda_common.cuh"
+
+namespace ttlda {
+
+// ---- generic rows: warp per row ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dirichlet_rows_warp_kernel(const double* __restrict__ a, int64_t rows,
+                                                                  int64_t cols, int64_t ld,
+                                                                  double* __restrict__ out_elog,
+                                                                  double* __restrict__ out_exp)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const double* row = a + r * ld;
+        double s = 0.;
+        for (int64_t j = lane; j < cols; j += 32) s += row[j];
+        s = warp_sum(s);
+        const double pt = psi_as103(s);
+        for (int64_t j = lane; j < ld; j += 32) {
+            const bool live = j < cols;
+            const double e = live ? psi_as103(row[j]) - pt : 0.;
+            if (out_elog) out_elog[r * ld + j] = e;
+            if (out_exp) out_exp[r * ld + j] = live ? exp(e) : 0.;
+        }
+    }
+}
+
+// ---- long rows: CTA per row ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dirichlet_rows_block_kernel(const double* __restrict__ a, int64_t rows,
+                                                                   int64_t cols, int64_t ld,
+                                                                   double* __restrict__ out_elog,
+                                                                   double* __restrict__ out_exp)
+{
+    __shared__ double sm[32];
+    __shared__ double s_pt;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double* row = a + r * ld;
+        double v[1] = {0.};
+        for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) v[0] += row[j];
+        block_sum<1>(v, sm);
+        if (threadIdx.x == 0) s_pt = psi_as103(v[0]);
+        __syncthreads();
+        const double pt = s_pt;
+        for (int64_t j = threadIdx.x; j < ld; j += blockDim.x) {
+            const bool live = j < cols;
+            const double e = live ? psi_as103(row[j]) - pt : 0.;
+            if (out_elog) out_elog[r * ld + j] = e;
+            if (out_exp) out_exp[r * ld + j] = live ? exp(e) : 0.;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void dirichlet_1d_kernel(double* __restrict__ doc_topic, double prior, double* __restrict__ out, int64_t n)
+{
+    __shared__ double sm[32];
+    __shared__ double s_pt;
+    double v[1] = {0.};
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double dt = doc_topic[i] + prior;  // cutils.pyx:31-33 (in-place prior add)
+        doc_topic[i] = dt;
+        v[0] += dt;
+    }
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) s_pt = psi_as103(v[0]);
+    __syncthreads();
+    const double pt = s_pt;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = exp(psi_as103(doc_topic[i]) - pt);
+}
+
+// ---- theta refresh: eT = exp(DE(gamma)), theta-prior term ------------------------------------------------------
+// One warp per document; lane l owns topics l, l+32, ...  Partial record per CTA -> fixed-order final reduction.
+__global__ void __launch_bounds__(256) theta_refresh_kernel(const double* __restrict__ gamma, int64_t D, int K,
+                                                            int64_t ld, const double* __restrict__ alpha_vec,
+                                                            double alpha_sum, double* __restrict__ eT,
+                                                            double* __restrict__ records)
+{
+    __shared__ double sm[32];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    // per-warp constants: sum_k lgamma(alpha_k), lgamma(sum(alpha))
+    double lga = 0.;
+    for (int k = lane; k < K; k += 32) lga += lgamma(alpha_vec[k]);
+    lga = warp_sum(lga);
+    const double lg_asum = lgamma(alpha_sum);
+    double term = 0.;
+    for (int64_t d = warp0; d < D; d += nwarps) {
+        const double* g = gamma + d * ld;
+        double s = 0.;
+        for (int k = lane; k < K; k += 32) s += g[k];
+        s = warp_sum(s);
+        const double pt = psi_as103(s);
+        double t = 0.;
+        for (int k = lane; k < (int)ld; k += 32) {
+            if (k < K) {
+                const double gk = g[k];
+                const double e = psi_as103(gk) - pt;
+                t += (alpha_vec[k] - gk) * e + lgamma(gk);
+                if (eT) eT[d * ld + k] = exp(e);
+            } else if (eT) {
+                eT[d * ld + k] = 0.;
+            }
+        }
+        t = warp_sum(t);
+        term += t - lga + (lg_asum - lgamma(s));
+    }
+    double v[1] = {lane == 0 ? term : 0.};
+    block_sum<1>(v, sm);
+    if (threadIdx.x == 0) {
+        double* rec = records + (size_t)blockIdx.x * NPART;
+        rec[0] = v[0];
+#pragma unroll
+        for (int j = 1; j < NPART; ++j) rec[j] = 0.;
+    }
+}
+
+// ---- exact-digamma statistics ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hyper_stats_kernel(const double* __restrict__ x, int64_t rows, int64_t cols,
+                                                          int64_t ld, double* __restrict__ records)
+{
+    __shared__ double sm[2 * 32];
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double a = 0., b = 0.;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const double* row = x + r * ld;
+        double s = 0., p = 0.;
+        for (int64_t j = lane; j < cols; j += 32) {
+            const double v = row[j];
+            s += v;
+            p += psi_exact(v);
+        }
+        s = warp_sum(s);
+        a += p;
+        if (lane == 0) b += psi_exact(s);
+    }
+    double v[2] = {a, b};
+    block_sum<2>(v, sm);
+    if (threadIdx.x == 0) {
+        double* rec = records + (size_t)blockIdx.x * NPART;
+        rec[0] = v[0];
+        rec[1] = v[1];
+#pragma unroll
+        for (int j = 2; j < NPART; ++j) rec[j] = 0.;
+    }
+}
+
+__global__ void psi_exact_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = psi_exact(x[i]);
+}
+
+}  // namespace ttlda
+
+using namespace ttlda;
+
+extern "C" {
+
+int ttlda_dirichlet_expectation_f64(const double* a, int64_t rows, int64_t cols, int64_t ld, double* out_elog,
+                                    double* out_exp, void* stream)
+{
+    TTLDA_REQUIRE(a != nullptr, "a is NULL");
+    TTLDA_REQUIRE(out_elog || out_exp, "both outputs NULL");
+    TTLDA_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols, "bad shape");
+    if (rows == 0 || ld == 0) return TTLDA_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (cols <= 2048) {
+        int grid = grid_for_warps(rows, 8, 8);
+        dirichlet_rows_warp_kernel<<<grid, 256, 0, s>>>(a, rows, cols, ld, out_elog, out_exp);
+    } else {
+        int grid = (int)(rows < (int64_t)kSMs * 8 ? rows : (int64_t)kSMs * 8);
+        dirichlet_rows_block_kernel<<<grid, 256, 0, s>>>(a, rows, cols, ld, out_elog, out_exp);
+    }
+    TTLDA_LAUNCH_CHECK("dirichlet_expectation");
+    return TTLDA_OK;
+}
+
+int ttlda_dirichlet_expectation_1d_f64(double* doc_topic, double prior, double* out, int64_t size, void* stream)
+{
+    TTLDA_REQUIRE(doc_topic && out, "NULL pointer");
+    TTLDA_REQUIRE(size >= 0, "negative size");
+    if (size == 0) return TTLDA_OK;
+    dirichlet_1d_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(doc_topic, prior, out, size);
+    TTLDA_LAUNCH_CHECK("dirichlet_expectation_1d");
+    return TTLDA_OK;
+}
+
+int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t ld, const double* alpha_vec,
+                            double alpha_sum, double* exp_elogtheta, double* partial_out, void* workspace,
+                            int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(gamma && alpha_vec && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(D >= 0 && K >= 1 && ld >= K && ld % 4 == 0, "bad shape");
+    if (workspace_bytes < reduce_ws_bytes()) {
+        set_error("theta_refresh: workspace %lld < %lld", (long long)workspace_bytes, (long long)reduce_ws_bytes());
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = grid_for_warps(D, 8, 8);
+    theta_refresh_kernel<<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta,
+                                             (double*)workspace);
+    TTLDA_LAUNCH_CHECK("theta_refresh");
+    return launch_reduce_records((const double*)workspace, grid, partial_out, s);
+}
+
+int ttlda_hyper_stats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* partial_out,
+                          void* workspace, int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(x && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols, "bad shape");
+    if (workspace_bytes < reduce_ws_bytes()) {
+        set_error("hyper_stats: workspace too small");
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = grid_for_warps(rows, 8, 8);
+    hyper_stats_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ld, (double*)workspace);
+    TTLDA_LAUNCH_CHECK("hyper_stats");
+    return launch_reduce_records((const double*)workspace, grid, partial_out, s);
+}
+
+int ttlda_psi_f64(const double* x, int64_t n, double* out, void* stream)
+{
+    TTLDA_REQUIRE(x && out, "NULL pointer");
+    if (n <= 0) return TTLDA_OK;
+    int grid = (int)((n + 255) / 256 < (int64_t)kSMs * 8 ? (n + 255) / 256 : (int64_t)kSMs * 8);
+    psi_exact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+    TTLDA_LAUNCH_CHECK("psi");
+    return TTLDA_OK;
+}
+
+}  // extern "C"

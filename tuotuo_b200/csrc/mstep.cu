@@ -1,0 +1,195 @@
+// mstep.cu — M-step on the word-major tables: lambda = eta + sstats * exp(E[log beta]); Dirichlet expectation of the
+// new lambda over the vocabulary; exp of it; beta-prior ELBO term.
+//
+// Reference: `lambda_update *= np.exp(expec_log_beta)` tuotuo/lda_model.py:264; LDASmoothed.m_step :273-283;
+// _dirichlet_expectation_2d tuotuo/cutils.pyx:41-68 (row k of the reference's (K,V) lambda is column k here);
+// expec_real_dist_minus_suro_dist(Elogbeta, eta, lambda) :25-46 with call site :157-163.
+//
+// Three HBM-streaming kernels over the [V][ld] tables (K*V*8 bytes each, coalesced, read/written once):
+//   1. mstep_lambda_kernel  : lambda = eta + S*eB, per-CTA column partial sums
+//   2. colsum_finish_kernel : column sums in fixed CTA order, psi~(colsum_k), sum_k (lgamma(eta_sum) - lgamma(colsum_k))
+//   3. beta_refresh_kernel  : Elogbeta = psi~(lambda) - psi~(colsum), eB = exp(Elogbeta), beta-prior term records
+#include "ttlda_common.cuh"
+
+namespace ttlda {
+
+constexpr int kColBlocks = 592;  // 148 SMs x 4: CTAs of the column-sum pass (fixed => reproducible partial order)
+constexpr int kMaxJ = 8;         // columns per thread: ld <= TX * kMaxJ with TX >= 128 for ld > 64
+
+// blockDim = (TX, 256/TX).  Thread (tx,ty) owns columns k = tx + TX*j and words w0+ty, w0+ty+TY, ...
+template <bool FROM_SSTATS>
+__global__ void __launch_bounds__(256) mstep_lambda_kernel(const double* __restrict__ S, const double* __restrict__ eB,
+                                                           double* __restrict__ lambda, int64_t V, int K, int64_t ld,
+                                                           double eta, double* __restrict__ colpart)
+{
+    extern __shared__ double sm_cols[];  // [TY][ld]
+    const int TX = blockDim.x, TY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t per = (V + gridDim.x - 1) / gridDim.x;
+    const int64_t w0 = (int64_t)blockIdx.x * per, w1 = (w0 + per < V) ? w0 + per : V;
+    double cs[kMaxJ];
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) cs[j] = 0.;
+    for (int64_t w = w0 + ty; w < w1; w += TY) {
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) {
+            const int k = tx + TX * j;
+            if (k < (int)ld) {
+                const int64_t idx = w * ld + k;
+                double lam;
+                if (FROM_SSTATS) {
+                    lam = (k < K) ? eta + S[idx] * eB[idx] : 0.;  // lda_model.py:264 then :280
+                    lambda[idx] = lam;
+                } else {
+                    lam = (k < K) ? lambda[idx] : 0.;
+                }
+                cs[j] += lam;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) {
+        const int k = tx + TX * j;
+        if (k < (int)ld) sm_cols[ty * ld + k] = cs[j];
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) {
+            const int k = tx + TX * j;
+            if (k < (int)ld) {
+                double s = 0.;
+                for (int y = 0; y < TY; ++y) s += sm_cols[y * ld + k];
+                colpart[(int64_t)blockIdx.x * ld + k] = s;
+            }
+        }
+    }
+}
+
+// colsum[k], psi~(colsum[k]) and the third ELBO term; single CTA.
+__global__ void colsum_finish_kernel(const double* __restrict__ colpart, int nblocks, int K, int64_t ld,
+                                     double eta_sum, double* __restrict__ colsum, double* __restrict__ psi_colsum,
+                                     double* __restrict__ extra)
+{
+    __shared__ double sm[32];
+    double t[1] = {0.};
+    const double lg_eta_sum = lgamma(eta_sum);
+    for (int k = threadIdx.x; k < (int)ld; k += blockDim.x) {
+        double s = 0.;
+        for (int b = 0; b < nblocks; ++b) s += colpart[(int64_t)b * ld + k];
+        colsum[k] = s;
+        if (k < K) {
+            psi_colsum[k] = psi_as103(s);  // cutils.pyx:63
+            t[0] += lg_eta_sum - lgamma(s);  // lda_model.py:42-44
+        } else {
+            psi_colsum[k] = 0.;
+        }
+    }
+    block_sum<1>(t, sm);
+    if (threadIdx.x == 0) extra[0] = t[0];
+}
+
+__global__ void __launch_bounds__(256) beta_refresh_kernel(const double* __restrict__ lambda, int64_t V, int K,
+                                                           int64_t ld, double eta, const double* __restrict__ psi_colsum,
+                                                           const double* __restrict__ extra, double* __restrict__ eB,
+                                                           double* __restrict__ elogbeta, double* __restrict__ records)
+{
+    __shared__ double sm[32];
+    const int64_t total = V * ld;
+    const double lg_eta = lgamma(eta);
+    double t[1] = {0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ld);
+        double e = 0., x = 0.;
+        if (k < K) {
+            const double lam = lambda[i];
+            e = psi_as103(lam) - psi_colsum[k];        // cutils.pyx:65-66
+            x = exp(e);
+            t[0] += (eta - lam) * e + (lgamma(lam) - lg_eta);  // lda_model.py:40-41
+        }
+        eB[i] = x;
+        if (elogbeta) elogbeta[i] = e;
+    }
+    block_sum<1>(t, sm);
+    if (threadIdx.x == 0) {
+        double* rec = records + (size_t)blockIdx.x * NPART;
+        rec[0] = t[0] + (blockIdx.x == 0 ? extra[0] : 0.);
+#pragma unroll
+        for (int j = 1; j < NPART; ++j) rec[j] = 0.;
+    }
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+static int64_t mstep_ws_bytes(int64_t ld)
+{
+    return (int64_t)(align256((size_t)reduce_ws_bytes()) + align256((size_t)kColBlocks * ld * sizeof(double)) +
+                     align256((size_t)ld * sizeof(double)) + 256);
+}
+
+template <bool FROM_SSTATS>
+static int run_mstep(const double* S, int64_t V, int64_t K, int64_t ld, double eta, double* eB, double* lambda,
+                     double* elogbeta, double* colsum_out, double* partial_out, void* workspace,
+                     int64_t workspace_bytes, cudaStream_t s)
+{
+    if (workspace_bytes < mstep_ws_bytes(ld)) {
+        set_error("mstep: workspace %lld < %lld", (long long)workspace_bytes, (long long)mstep_ws_bytes(ld));
+        return TTLDA_EWORKSPACE;
+    }
+    char* ws = (char*)workspace;
+    double* records = (double*)ws;
+    double* colpart = (double*)(ws + align256((size_t)reduce_ws_bytes()));
+    double* psi_colsum = (double*)((char*)colpart + align256((size_t)kColBlocks * ld * sizeof(double)));
+    double* extra = (double*)((char*)psi_colsum + align256((size_t)ld * sizeof(double)));
+
+    int TX = 32;
+    while (TX < 256 && TX < ld) TX *= 2;
+    if (ld > 64 && TX < 128) TX = 128;
+    const int TY = 256 / TX;
+    int nblocks = (int)(V < kColBlocks ? (V > 0 ? V : 1) : kColBlocks);
+    const size_t smem = (size_t)TY * ld * sizeof(double);
+    mstep_lambda_kernel<FROM_SSTATS><<<nblocks, dim3(TX, TY), smem, s>>>(S, eB, lambda, V, (int)K, ld, eta, colpart);
+    TTLDA_LAUNCH_CHECK("mstep_lambda");
+    // eta is a scalar prior: np.sum(eta) is eta itself
+    colsum_finish_kernel<<<1, 256, 0, s>>>(colpart, nblocks, (int)K, ld, eta, colsum_out, psi_colsum, extra);
+    TTLDA_LAUNCH_CHECK("colsum_finish");
+    const int64_t total = V * ld;
+    int grid = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
+    if (grid < 1) grid = 1;
+    beta_refresh_kernel<<<grid, 256, 0, s>>>(lambda, V, (int)K, ld, eta, psi_colsum, extra, eB, elogbeta, records);
+    TTLDA_LAUNCH_CHECK("beta_refresh");
+    return launch_reduce_records(records, grid, partial_out, s);
+}
+
+}  // namespace ttlda
+
+using namespace ttlda;
+
+extern "C" {
+
+int64_t ttlda_mstep_workspace_bytes(int64_t V, int64_t ld)
+{
+    (void)V;
+    return mstep_ws_bytes(ld);
+}
+
+int ttlda_mstep_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, double eta, double* exp_elogbeta,
+                    double* lambda, double* elogbeta_out, double* colsum_out, double* partial_out, void* workspace,
+                    int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(sstats && exp_elogbeta && lambda && colsum_out && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(V >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
+    return run_mstep<true>(sstats, V, K, ld, eta, exp_elogbeta, lambda, elogbeta_out, colsum_out, partial_out,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t ld, double eta, double* exp_elogbeta,
+                           double* elogbeta_out, double* colsum_out, double* partial_out, void* workspace,
+                           int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(lambda && exp_elogbeta && colsum_out && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(V >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
+    return run_mstep<false>(nullptr, V, K, ld, eta, exp_elogbeta, const_cast<double*>(lambda), elogbeta_out,
+                            colsum_out, partial_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

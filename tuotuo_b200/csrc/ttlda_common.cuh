@@ -1,0 +1,131 @@
+// ttlda_common.cuh — shared device helpers for libttlda (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ttlda.h"
+
+namespace ttlda {
+
+// ---------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define TTLDA_REQUIRE(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            ::ttlda::set_error("%s: %s", __func__, msg);           \
+            return TTLDA_EINVAL;                                   \
+        }                                                          \
+    } while (0)
+
+#define TTLDA_LAUNCH_CHECK(what)                                   \
+    do {                                                           \
+        cudaError_t e__ = cudaGetLastError();                      \
+        if (e__ != cudaSuccess) return ::ttlda::cuda_fail(e__, what); \
+    } while (0)
+
+constexpr int kSMs = 148;             // B200: 2 dies x 74 SMs
+constexpr int kMaxReduceBlocks = 4096; // upper bound on the grid of any kernel that emits partial records
+constexpr int NPART = TTLDA_NPART;
+
+inline int64_t reduce_ws_bytes() { return (int64_t)kMaxReduceBlocks * NPART * sizeof(double); }
+
+// ---------------------------------------------------------------------------------------------------------
+// warp / block reductions (fixed order => bit-reproducible)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum `NV` values across the CTA; valid result in thread 0.  smem: double[NV * 32].
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* smem)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) smem[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double x = (lane < nwarps) ? smem[i * 32 + lane] : 0.0;
+            v[i] = warp_sum(x);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AS-103 digamma — op-for-op restatement of tuotuo/cutils.pyx:75-93 (the reference's "psi", optimised for speed
+// not accuracy).  Parity on gamma/lambda at 1e-9 requires this approximation, not an exact digamma.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double psi_as103(double x)
+{
+    if (x <= 1e-6) return -0.577215664901532860606512090082402431 - 1. / x;  // cutils.pyx:76-78
+    double result = 0.;
+    while (x < 6.) {  // cutils.pyx:83-85
+        result -= 1. / x;
+        x += 1.;
+    }
+    double r = 1. / x;  // cutils.pyx:89-92
+    result += log(x) - .5 * r;
+    r = r * r;
+    result -= r * ((1. / 12.) - r * ((1. / 120.) - r * (1. / 252.)));
+    return result;
+}
+
+// Exact digamma for x > 0 (recurrence to x >= 10, then the asymptotic series through x^-14; |err| ~ 1e-16
+// relative).  Used only where the reference calls scipy.special.psi (hyper-parameter Newton updates).
+__device__ __forceinline__ double psi_exact(double x)
+{
+    double shift = 0.;
+    while (x < 10.) {
+        shift -= 1. / x;
+        x += 1.;
+    }
+    const double z = 1. / (x * x);
+    double p = 8.33333333333333333333e-2;
+    p = p * z - 2.10927960927960927961e-2;
+    p = p * z + 7.57575757575757575758e-3;
+    p = p * z - 4.16666666666666666667e-3;
+    p = p * z + 3.96825396825396825397e-3;
+    p = p * z - 8.33333333333333333333e-3;
+    p = p * z + 8.33333333333333333333e-2;
+    return log(x) - 0.5 / x - z * p + shift;
+}
+
+// 16-byte global loads of a K-vector slice.  The beta tables are re-read by many documents: keep them on the
+// read-only path; streaming data (CSR arrays) goes through L1::no_allocate.
+__device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
+
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p)
+{
+    int v;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
+// final fixed-order reduction of per-CTA records: out[j] = sum_b rec[b][j]
+__global__ void reduce_records_kernel(const double* __restrict__ rec, int nrec, double* __restrict__ out);
+int launch_reduce_records(const double* rec, int nrec, double* out, cudaStream_t stream);
+
+inline int grid_for_warps(int64_t nwarps_needed, int warps_per_block, int blocks_per_sm)
+{
+    int64_t blocks = (nwarps_needed + warps_per_block - 1) / warps_per_block;
+    int64_t cap = (int64_t)kSMs * blocks_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace ttlda

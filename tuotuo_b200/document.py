@@ -1,0 +1,210 @@
+"""``Document`` — drop-in for tuotuo/document.py:9-50, backed by a device-resident CSR doc-term matrix.
+
+Same constructor, same attributes (``sample_docs, num_doc_population, sample_docs_list, vocab_doc_count_dict,
+vocab_doc_count_array, doc_vocab_count_array, vocab_to_idx, idx_to_vocab, doc_vocab_count_df, V, M``) and the
+same three summary prints (tuotuo/utils.py:104-105,120).  Differences, all forced by scale:
+
+* the vocabulary/token-id pass runs once on the host (ids = order of first appearance, tuotuo/utils.py:177-206,
+  bit-exact); counting is done on the GPU by ``ttlda_bow_to_csr``;
+* the dense matrices / DataFrame are materialised lazily, only when the attribute is read (small corpora);
+* extra constructors for corpora that never exist as text: ``from_token_ids``, ``from_csr``, ``from_dense``;
+* ``shard(rank, world)`` gives the contiguous document block a rank owns in multi-GPU runs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .text import text_pipeline
+
+
+class Document:
+    def __init__(self, sample_docs: dict, num_doc_population: int = None) -> None:
+        self.sample_docs = sample_docs
+        if not num_doc_population:  # document.py:26-29
+            self.num_doc_population = len(sample_docs)
+        else:
+            self.num_doc_population = num_doc_population
+
+        # process_documents(sample=False)  (utils.py:89-130)
+        docs_list = []
+        length = 0
+        for _, v in sample_docs.items():
+            toks = text_pipeline(v).split(" ")  # an empty document yields [''] like the reference
+            docs_list.append(toks)
+            length += len(toks)
+        print(f"There are {len(docs_list)} documents in the dataset after processing")
+        if len(sample_docs):
+            print(f"On average estimated document length is {round(length / len(sample_docs), 1)} "
+                  f"words per document after processing")
+
+        # get_vocab_from_docs + get_np_wct: ids by first appearance (utils.py:177-206)
+        vocab: dict = {}
+        ids = np.empty(length, dtype=np.int32)
+        offs = np.zeros(len(docs_list) + 1, dtype=np.int64)
+        n = 0
+        for i, doc in enumerate(docs_list):
+            for w in doc:
+                j = vocab.get(w)
+                if j is None:
+                    j = len(vocab)
+                    vocab[w] = j
+                ids[n] = j
+                n += 1
+            offs[i + 1] = n
+        print(f"There are {len(vocab)} unique vocab in the corpus after processing")
+
+        self.sample_docs_list = docs_list
+        self.vocab_to_idx = vocab
+        self.idx_to_vocab = {v: k for k, v in vocab.items()}
+        self.V = len(vocab)
+        self.M = len(docs_list)
+        self._token_ids, self._doc_offsets = ids, offs
+        self._host_csr = None
+        self._dev = {}
+
+    # -- alternative constructors ---------------------------------------------------------------------------------------
+    @classmethod
+    def _blank(cls, M, V, num_doc_population=None, idx_to_vocab=None):
+        self = cls.__new__(cls)
+        self.sample_docs = None
+        self.sample_docs_list = None
+        self.num_doc_population = num_doc_population if num_doc_population else M
+        self.M, self.V = int(M), int(V)
+        self.idx_to_vocab = idx_to_vocab if idx_to_vocab is not None else _LazyVocab(V)
+        self.vocab_to_idx = ({v: k for k, v in idx_to_vocab.items()} if isinstance(idx_to_vocab, dict) else None)
+        self._token_ids = self._doc_offsets = None
+        self._host_csr = None
+        self._dev = {}
+        return self
+
+    @classmethod
+    def from_token_ids(cls, token_ids, doc_offsets, V, num_doc_population=None, idx_to_vocab=None):
+        """token_ids: int32 vocabulary ids (NumPy or CUDA tensor); doc_offsets: int64[M+1]."""
+        self = cls._blank(len(doc_offsets) - 1, V, num_doc_population, idx_to_vocab)
+        self._token_ids, self._doc_offsets = token_ids, doc_offsets
+        return self
+
+    @classmethod
+    def from_csr(cls, rowptr, colidx, counts, V, num_doc_population=None, idx_to_vocab=None):
+        """Host CSR (NumPy): rowptr int64[M+1], colidx ascending per row, counts."""
+        self = cls._blank(len(rowptr) - 1, V, num_doc_population, idx_to_vocab)
+        self._host_csr = (np.ascontiguousarray(rowptr, dtype=np.int64), np.ascontiguousarray(colidx, dtype=np.int32),
+                          np.ascontiguousarray(counts, dtype=np.int32))
+        return self
+
+    @classmethod
+    def from_dense(cls, X, num_doc_population=None, idx_to_vocab=None):
+        """Dense M x V counts (the reference's doc_vocab_count_array) -> CSR.  Host-side format conversion."""
+        X = np.asarray(X)
+        rows, cols = np.nonzero(X)
+        rowptr = np.zeros(X.shape[0] + 1, dtype=np.int64)
+        np.add.at(rowptr, rows + 1, 1)
+        vals = X[rows, cols]
+        if not np.all(vals == np.round(vals)):
+            raise ValueError("count matrix must hold integers")
+        return cls.from_csr(np.cumsum(rowptr), cols, vals.astype(np.int32), X.shape[1], num_doc_population,
+                            idx_to_vocab)
+
+    # -- device side ---------------------------------------------------------------------------------------------------------
+    def device_corpus(self, device):
+        """The CSR/CSC doc-term matrix on `device` (built once per device)."""
+        import torch
+
+        from .corpus import DeviceCorpus
+
+        dev = torch.device(device)
+        key = str(dev)
+        if key not in self._dev:
+            if self._host_csr is not None:
+                self._dev[key] = DeviceCorpus.from_host_csr(*self._host_csr, self.V, dev)
+            else:
+                tok, offs = self._token_ids, self._doc_offsets
+                tok = tok if isinstance(tok, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(tok, dtype=np.int32))
+                offs = offs if isinstance(offs, torch.Tensor) else torch.as_tensor(
+                    np.ascontiguousarray(offs, dtype=np.int64))
+                self._dev[key] = DeviceCorpus.from_token_ids(tok.to(dev), offs.to(dev), self.V)
+        return self._dev[key]
+
+    def _default_corpus(self):
+        if self._dev:
+            return next(iter(self._dev.values()))
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("Document count matrices are built on the GPU (ttlda_bow_to_csr); no CUDA device found")
+        return self.device_corpus(torch.device("cuda", torch.cuda.current_device()))
+
+    def host_csr(self):
+        if self._host_csr is None:
+            self._host_csr = self._default_corpus().host_csr()
+        return self._host_csr
+
+    def shard(self, rank: int, world: int) -> "Document":
+        """Contiguous document block of `rank` out of `world` (token/nnz balanced)."""
+        from .corpus import balanced_doc_partition
+
+        if self._host_csr is not None:
+            rp, ci, ct = self._host_csr
+            b = balanced_doc_partition(rp, world)
+            lo, hi = int(b[rank]), int(b[rank + 1])
+            s, e = int(rp[lo]), int(rp[hi])
+            sub = Document.from_csr(rp[lo:hi + 1] - s, ci[s:e], ct[s:e], self.V, self.num_doc_population,
+                                    self.idx_to_vocab if isinstance(self.idx_to_vocab, dict) else None)
+        else:
+            import torch
+
+            offs = self._doc_offsets
+            offs_np = offs.cpu().numpy() if isinstance(offs, torch.Tensor) else np.asarray(offs)
+            b = balanced_doc_partition(offs_np, world)
+            lo, hi = int(b[rank]), int(b[rank + 1])
+            s, e = int(offs_np[lo]), int(offs_np[hi])
+            sub = Document.from_token_ids(self._token_ids[s:e], offs[lo:hi + 1] - s, self.V, self.num_doc_population,
+                                          self.idx_to_vocab if isinstance(self.idx_to_vocab, dict) else None)
+        sub.doc_range = (lo, hi)
+        return sub
+
+    # -- the reference's dense attributes, materialised on demand ---------------------------------------------------------------
+    @property
+    def doc_vocab_count_array(self) -> np.ndarray:  # document.py:36 (M x V, a transposed view there too)
+        return self.vocab_doc_count_array.T
+
+    @property
+    def vocab_doc_count_array(self) -> np.ndarray:  # document.py:35 (V x M float64)
+        if getattr(self, "_vd", None) is None:
+            rp, ci, ct = self.host_csr()
+            if self.M * self.V > 2 ** 31:
+                raise MemoryError("dense count matrix requested for a large corpus; use host_csr()")
+            vd = np.zeros((self.V, self.M), dtype=float)
+            vd[ci, np.repeat(np.arange(self.M), np.diff(rp))] = ct
+            self._vd = vd
+        return self._vd
+
+    @property
+    def vocab_doc_count_dict(self) -> dict:  # document.py:34: word -> list of per-document counts
+        vd = self.vocab_doc_count_array
+        return {self.idx_to_vocab[i]: [int(c) for c in vd[i]] for i in range(self.V)}
+
+    @property
+    def doc_vocab_count_df(self):  # document.py:41-44
+        import pandas as pd
+
+        return pd.DataFrame(data=self.doc_vocab_count_array, columns=[self.idx_to_vocab[i] for i in range(self.V)])
+
+
+class _LazyVocab:
+    """idx -> 'w<idx>' for synthetic corpora without strings (dict-like, no V-sized allocation)."""
+
+    def __init__(self, V):
+        self.V = int(V)
+
+    def __getitem__(self, i):
+        i = int(i)
+        if not 0 <= i < self.V:
+            raise KeyError(i)
+        return f"w{i}"
+
+    def __len__(self):
+        return self.V
+
+    def items(self):
+        return ((i, f"w{i}") for i in range(self.V))

@@ -1,0 +1,527 @@
+"""``LDASmoothed`` — drop-in for tuotuo/lda_model.py:49-564 whose batch variational-inference hot path runs as
+hand-written sm_100a kernels (``libttlda.so``, C ABI in ``include/ttlda.h``).
+
+Same constructor, same ``fit`` signature and control flow (initial perplexity, early ``return`` on a perplexity
+delta below ``threshold``, hyper-parameter Newton updates followed by one perplexity with the stale expectations),
+same prints, same attributes (``_lambda_`` (K,V), ``_gamma_`` (M,K), ``_alpha_``, ``_eta_``, ``K``, ``M``, ``V``,
+``train_doc``).  State lives on the GPU in word-major tables; the NumPy attributes are snapshots copied back on
+access.  There is NO CPU path: without a CUDA device / the built library every call raises.
+
+Per EM iteration (tuotuo/lda_model.py:285-316 + :403-409):
+    ttlda_estep_f64        gamma, exp(E[log theta]) refresh, theta-prior term        (e_step :197-270, :142-148)
+    ttlda_sstats_csc_f64   K x V sufficient statistics, word-major, no atomics       (:262)
+    [NCCL all_reduce]      documents are sharded across ranks; sum the statistics    
+    ttlda_mstep_f64        lambda, exp(E[log beta]) refresh, beta-prior term         (:264, m_step :273-283, :157-163)
+    ttlda_elbo_tokens_f64  token term of the ELBO at the new state                   (:125-139)
+and one 3-double device->host read for the perplexity / convergence test.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+import torch
+from scipy.special import polygamma, psi
+
+from . import _native as nv
+from .corpus import DeviceCorpus
+from .document import Document
+
+SEED = 42  # lda_model.py:19
+DTYPE = float  # lda_model.py:20
+
+
+def np_clip_for_exp(x, sub: float = 1e-05):
+    """tuotuo/utils.py:20-26."""
+    if x > 0:
+        x = max(sub, x)
+    elif x < 0:
+        x = min(sub, x)
+    return x
+
+
+class _State:
+    """Device tensors of one fit."""
+    pass
+
+
+class LDASmoothed:
+    """Smoothed LDA, batch variational inference (drop-in for tuotuo.lda_model.LDASmoothed)."""
+
+    def __init__(self, num_topics: int, exchangeable_prior: bool = True, verbose: bool = True, *,
+                 device=None, sstats_mode: str = "csc") -> None:
+        self.K = num_topics
+        np.random.seed(SEED)  # lda_model.py:71 (global side effect, kept)
+        if exchangeable_prior:
+            self._alpha_ = 1
+        else:
+            self._alpha_ = np.random.gamma(shape=100, scale=0.01, size=(1, self.K))
+        if verbose:
+            print(f"Topic Dirichlet Prior, α")
+            print(self._alpha_)
+            print()
+        self._eta_ = 1
+        if verbose:
+            print(f"Exchangeable Word Dirichlet Prior, Eta ")
+            print(self._eta_)
+            print()
+        if sstats_mode not in ("csc", "atomic"):
+            raise ValueError("sstats_mode must be 'csc' (two-pass, reproducible) or 'atomic' (one pass, red.f64)")
+        self._sstats_mode = sstats_mode
+        self._device = device
+        self._st = None
+        self._np_cache = {}
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # device plumbing
+    # ------------------------------------------------------------------------------------------------------------------
+    def _dev(self) -> torch.device:
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise nv.TTLDAError("LDASmoothed needs a CUDA device (sm_100a); there is no CPU fallback")
+            self._device = torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self._device)
+
+    @staticmethod
+    def _dist():
+        import torch.distributed as dist
+
+        return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+
+    def _as_document(self, train_doc) -> Document:
+        if isinstance(train_doc, Document):
+            return train_doc
+        if isinstance(train_doc, dict):  # readme.md:42-47 passes the raw dict
+            return Document(train_doc)
+        if isinstance(train_doc, np.ndarray):
+            return Document.from_dense(train_doc)
+        if hasattr(train_doc, "doc_vocab_count_array"):  # the reference's own Document, or a duck type
+            return Document.from_dense(np.asarray(train_doc.doc_vocab_count_array),
+                                       getattr(train_doc, "num_doc_population", None),
+                                       getattr(train_doc, "idx_to_vocab", None))
+        raise TypeError(f"cannot build a corpus from {type(train_doc)}")
+
+    def _alpha_vec_host(self) -> np.ndarray:
+        return np.ascontiguousarray(
+            np.broadcast_to(np.asarray(self._alpha_, dtype=np.float64).reshape(-1), (self.K,)))
+
+    def _alpha_sum(self) -> float:
+        # np.sum(real_dist_prior) at lda_model.py:43 — a scalar prior sums to itself
+        return float(np.sum(self._alpha_))
+
+    def _upload_alpha(self):
+        st = self._st
+        st.alpha_vec = torch.as_tensor(self._alpha_vec_host()).to(st.dev)
+
+    def _alloc_state(self, corpus: DeviceCorpus):
+        dev = corpus.device
+        nv.check_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        K, V, D = int(self.K), corpus.V, corpus.D
+        if not 1 <= K <= nv.MAX_K:
+            raise ValueError(f"num_topics must be in [1, {nv.MAX_K}]")
+        ld = nv.ld_for(K)
+        st = _State()
+        st.dev, st.corpus, st.K, st.V, st.D, st.ld = dev, corpus, K, V, D, ld
+        f64 = torch.float64
+        st.gamma = torch.zeros((D, ld), dtype=f64, device=dev)
+        st.eT = [torch.zeros((D, ld), dtype=f64, device=dev), torch.zeros((D, ld), dtype=f64, device=dev)]
+        st.cur = 0
+        st.lam = torch.zeros((V, ld), dtype=f64, device=dev)
+        st.eB = torch.zeros((V, ld), dtype=f64, device=dev)
+        st.sstats = torch.zeros((V, ld), dtype=f64, device=dev)
+        st.colsum = torch.zeros(ld, dtype=f64, device=dev)
+        st.part = torch.zeros((4, nv.NPART), dtype=f64, device=dev)
+        st.iters = torch.zeros(2, dtype=torch.int64, device=dev)
+        st.ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
+        st.ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
+        st.ws_s = (torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld), dtype=torch.uint8, device=dev)
+                   if self._sstats_mode == "csc" else None)
+        st.terms = dict(tok=0.0, theta=0.0, beta=0.0, count=0.0)
+        self._st = st
+        self._np_cache = {}
+        self._upload_alpha()
+        return st
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # NumPy views of the device state (snapshots)
+    # ------------------------------------------------------------------------------------------------------------------
+    @property
+    def _lambda_(self) -> np.ndarray:
+        if self._st is None:
+            raise AttributeError("'LDASmoothed' object has no attribute '_lambda_'")
+        if "lam" not in self._np_cache:
+            st = self._st
+            out = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
+            nv.transpose_unpad(st.lam, st.K, out)
+            self._np_cache["lam"] = out.cpu().numpy()
+        return self._np_cache["lam"]
+
+    @_lambda_.setter
+    def _lambda_(self, value):
+        st = self._st
+        if st is None:
+            raise AttributeError("fit() first")
+        v = torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64)).to(st.dev)
+        assert v.shape == (st.K, st.V)
+        nv.transpose_pad(v, st.lam)
+        self._np_cache.pop("lam", None)
+
+    @property
+    def _gamma_(self) -> np.ndarray:
+        if self._st is None:
+            raise AttributeError("'LDASmoothed' object has no attribute '_gamma_'")
+        if "gamma" not in self._np_cache:
+            st = self._st
+            local = st.gamma[:, :st.K].contiguous()
+            dist = self._dist()
+            if dist is not None:  # gather the document shards in rank order
+                sizes = [torch.zeros(1, dtype=torch.int64, device=st.dev) for _ in range(dist.get_world_size())]
+                dist.all_gather(sizes, torch.tensor([st.D], dtype=torch.int64, device=st.dev))
+                mx = int(max(int(s.item()) for s in sizes))
+                pad = torch.zeros((mx, st.K), dtype=torch.float64, device=st.dev)
+                pad[:st.D] = local
+                parts = [torch.empty_like(pad) for _ in sizes]
+                dist.all_gather(parts, pad)
+                local = torch.cat([p[:int(s.item())] for p, s in zip(parts, sizes)], 0)
+            self._np_cache["gamma"] = local.cpu().numpy()
+        return self._np_cache["gamma"]
+
+    @_gamma_.setter
+    def _gamma_(self, value):
+        st = self._st
+        if st is None:
+            raise AttributeError("fit() first")
+        v = torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64)).to(st.dev)
+        assert v.shape == (st.D, st.K)
+        st.gamma.zero_()
+        st.gamma[:, :st.K] = v
+        self._np_cache.pop("gamma", None)
+
+    def _invalidate(self, *names):
+        for n in names or ("lam", "gamma"):
+            self._np_cache.pop(n, None)
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # device-level steps
+    # ------------------------------------------------------------------------------------------------------------------
+    def _refresh_theta(self):
+        st = self._st
+        nv.theta_refresh(st.gamma, st.K, st.alpha_vec, self._alpha_sum(), st.eT[st.cur], st.part[1], st.ws)
+
+    def _refresh_theta_term_only(self):
+        st = self._st
+        nv.theta_refresh(st.gamma, st.K, st.alpha_vec, self._alpha_sum(), None, st.part[1], st.ws)
+
+    def _refresh_beta(self):
+        st = self._st
+        nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB, None, st.colsum, st.part[2], st.ws_m)
+
+    def _tokens(self):
+        st, c = self._st, self._st.corpus
+        nv.elbo_tokens(c.rowptr, c.colidx, c.counts, st.K, st.eT[st.cur], st.eB, st.part[3], st.ws)
+
+    def _em_iteration(self, e_num_step: int, e_threshold: float = 1e-05):
+        """One em_step (lda_model.py:285-316) followed by the token term of the next perplexity."""
+        st, c = self._st, self._st.corpus
+        cur, nxt = st.cur, st.cur ^ 1
+        atomic = self._sstats_mode == "atomic"
+        if atomic:
+            st.sstats.zero_()
+        nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
+                 st.gamma, st.eT[nxt], st.sstats if atomic else None, e_num_step, e_threshold, st.iters, st.part[0],
+                 st.ws)
+        if not atomic:
+            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, st.eT[cur], st.eB, st.sstats, st.ws_s)
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink
+        nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
+        st.cur = nxt
+        self._tokens()
+        self._invalidate()
+
+    def _collect(self, theta_row: int):
+        """One device->host read of the ELBO terms (summed over ranks when sharded)."""
+        st = self._st
+        buf = torch.stack([st.part[3, 0], st.part[theta_row, 1 if theta_row == 0 else 0], st.part[3, 2],
+                           st.iters[0].to(torch.float64), st.iters[1].to(torch.float64), st.part[2, 0]])
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(buf[:5])  # the beta term (entry 5) is replicated, not sharded
+        h = buf.cpu().numpy()
+        st.terms = dict(tok=float(h[0]), theta=float(h[1]), beta=float(h[5]), count=float(h[2]))
+        return int(h[3]), int(h[4])
+
+    def _perplexity_from_terms(self, sampling: bool) -> float:
+        t = self._st.terms
+        elbo = t["tok"] + t["theta"]  # document-dependent part (lda_model.py:125-148)
+        total = t["count"]
+        if sampling:  # lda_model.py:152-153,187-188
+            scale = self.D_population / self._num_doc_global
+            elbo = elbo * scale
+            total = total * scale
+        elbo += t["beta"]  # :157-163
+        self._last_elbo = elbo
+        return float(np.exp(np_clip_for_exp(-elbo / total)))
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # fit  (lda_model.py:318-432)
+    # ------------------------------------------------------------------------------------------------------------------
+    def fit(self, train_doc, sampling: bool = False, threshold: float = 1e-05, em_num_step: int = 100,
+            e_num_step: int = 100, newton_num_step: int = 100, update_hyper_parms: bool = True, batch: bool = True,
+            verbose=False, return_perplexities: bool = False):
+        train_doc = self._as_document(train_doc)
+        corpus = train_doc.device_corpus(self._dev())
+        dist = self._dist()
+        n_docs = corpus.D
+        if dist is not None:
+            t = torch.tensor([corpus.D], dtype=torch.int64, device=corpus.device)
+            dist.all_reduce(t)
+            n_docs = int(t.item())
+        if not hasattr(self, "train_doc"):  # lda_model.py:340-348 (cached on first call only)
+            self.train_doc = train_doc
+        if not hasattr(self, "M"):
+            self.M = n_docs
+        if not hasattr(self, "V"):
+            self.V = train_doc.V
+        if self.V != train_doc.V or self.M != n_docs:
+            raise ValueError("fit() was first called with a corpus of a different shape (M, V are cached like the "
+                             "reference does, lda_model.py:340-348); create a new LDASmoothed")
+        self._num_doc_global = n_docs
+        if sampling and not hasattr(self, "D_population"):
+            # the reference reads self.D_population without ever assigning it (AttributeError);
+            # the only population size it knows is Document.num_doc_population — use it.
+            self.D_population = train_doc.num_doc_population
+
+        st = self._alloc_state(corpus)
+        K, V = st.K, st.V
+
+        np.random.seed(SEED)  # lda_model.py:356-357: legacy MT19937 gamma stream, generated on the host
+        lam0 = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(DTYPE, copy=False)
+        nv.transpose_pad(torch.as_tensor(lam0).to(st.dev), st.lam)
+        if verbose:
+            print(f"Var Inf - Word Dirichlet prior, Lambda")
+            print((K, V))
+            print()
+        st.gamma.zero_()  # lda_model.py:364: alpha + ones * V / K
+        st.gamma[:, :K] = st.alpha_vec + float(V) / float(K)
+        if verbose:
+            print(f"Var Inf - Topic Dirichlet prior, Gamma")
+            print((self.M, K))
+            print()
+
+        perplexities = []
+        self._refresh_theta()
+        self._refresh_beta()
+        self._tokens()
+        self._collect(theta_row=1)
+        perplexity = self._perplexity_from_terms(sampling)  # lda_model.py:373-378
+        perplexities.append(np.float64(perplexity))
+        if verbose:
+            print(f"Init perplexity = {perplexity}")
+
+        delta_perplexity = np.inf
+        for _ in range(em_num_step):  # lda_model.py:384
+            if delta_perplexity < threshold:  # :386-390 early return, skips the hyper-parameter update
+                return perplexities if return_perplexities else None
+            perplexity_orig = perplexity
+            self._em_iteration(e_num_step)
+            _, capped = self._collect(theta_row=0)
+            if capped:
+                warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
+            perplexity = self._perplexity_from_terms(sampling)  # :403-409
+            perplexities.append(np.float64(perplexity))
+            delta_perplexity = perplexity_orig - perplexity
+
+        if update_hyper_parms:  # lda_model.py:414-424
+            self.update_alpha()
+            self.update_eta()
+            # perplexity with the *stale* expectations and the new alpha / eta: only the prior terms change
+            # (exp(E[log beta]) is rewritten with identical values: it does not depend on eta)
+            self._refresh_theta_term_only()
+            self._refresh_beta()
+            self._collect(theta_row=1)
+            perplexity = self._perplexity_from_terms(sampling)
+            perplexities.append(np.float64(perplexity))
+
+        if verbose:
+            print(f"End perplexity = {perplexities[-1]}")
+        return perplexities if return_perplexities else None
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # hyper-parameter Newton updates (lda_model.py:435-554): device reductions with an exact digamma, scalar
+    # Newton on the host
+    # ------------------------------------------------------------------------------------------------------------------
+    def _gamma_psi_stat(self) -> float:
+        """sum_dk psi(gamma_dk) - K * sum_d psi(sum_k gamma_dk)   (loop-invariant part of lda_model.py:459-462)."""
+        st = self._st
+        nv.hyper_stats(st.gamma, st.K, st.part[1], st.ws)
+        v = st.part[1, :2].clone()
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(v)
+        h = v.cpu().numpy()
+        return float(h[0] - st.K * h[1])
+
+    def _lambda_psi_stat(self) -> float:
+        """sum_kv psi(lambda_kv) - V * sum_k psi(sum_v lambda_kv)   (lda_model.py:522-528)."""
+        st = self._st
+        nv.hyper_stats(st.lam, st.K, st.part[1], st.ws)
+        pc = torch.empty(st.K, dtype=torch.float64, device=st.dev)
+        nv.psi_exact(st.colsum[:st.K].contiguous(), pc)
+        return float(st.part[1, 0].item() - st.V * pc.sum().item())
+
+    def update_alpha(self, step: int = 500, threshold: float = 1e-07, verbose: bool = False) -> None:
+        if isinstance(self._alpha_, np.ndarray):
+            # the reference's non-exchangeable branch (lda_model.py:452-456,464-476) diverges
+            raise NotImplementedError("update_alpha for a non-exchangeable prior is numerically broken in the "
+                                      "reference (diverges) and is not reproduced; use update_hyper_parms=False")
+        stat = self._gamma_psi_stat()
+        M, K = self.M, self.K
+        it = 0
+        while it <= step:
+            g = M * K * (psi(K * self._alpha_) - psi(self._alpha_)) + stat  # :459-462
+            h = M * K * (K * polygamma(1, K * self._alpha_) - polygamma(1, self._alpha_))  # :479
+            alpha_new = self._alpha_ - g / h
+            delta = np.sum(np.abs(alpha_new - self._alpha_))
+            if verbose:
+                print(f"M Step: Iteration {it}, Delta Alpha = {delta}")
+                print(f"Alpha Old:{self._alpha_} -> Alpha New:{alpha_new}")
+            self._alpha_ = alpha_new
+            it += 1
+            if delta < threshold:
+                self._upload_alpha()
+                return
+        self._upload_alpha()
+        warnings.warn(f"Update alphda Maximum iteration reached at step {it}")
+
+    def update_eta(self, step: int = 1000, threshold: float = 1e-09, verbose: bool = False) -> None:
+        stat = self._lambda_psi_stat()
+        K, V = self.K, self.V
+        it = 0
+        while it <= step:
+            g = K * V * (psi(V * self._eta_) - psi(self._eta_)) + stat  # :525-528
+            h = K * V * (V * polygamma(1, V * self._eta_) - polygamma(1, self._eta_))  # :531
+            eta_new = self._eta_ - g / h
+            if eta_new < 0:
+                raise ValueError(f"Dirichlet Parameter become < 0 at iteration {it}")
+            delta = np.abs(eta_new - self._eta_)
+            if verbose:
+                print(f"M Step: delta eta is {delta}")
+                print(f"Eta Old {self._eta_} -> Eta New {eta_new}")
+            self._eta_ = eta_new
+            it += 1
+            if delta < threshold:
+                return
+        warnings.warn(f"Update Eta: Maximum iteration reached at step {it}")
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # reference-shaped step API (NumPy in / NumPy out); thin wrappers over the same kernels
+    # ------------------------------------------------------------------------------------------------------------------
+    def _elog_np(self):
+        st = self._st
+        et = torch.empty_like(st.gamma)
+        nv.dirichlet_expectation(st.gamma, st.K, out_elog=et)
+        eb = torch.empty_like(st.lam)
+        self_colwise = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
+        nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB.clone(), eb, st.colsum, st.part[2], st.ws_m)
+        nv.transpose_unpad(eb, st.K, self_colwise)
+        return et[:, :st.K].cpu().numpy(), self_colwise.cpu().numpy()
+
+    def _check_X(self, X):
+        if X is not None and self._st is not None:
+            shape = getattr(X, "shape", None)
+            if shape is not None and tuple(shape) != (self._st.D, self._st.V):
+                raise ValueError("X does not match the fitted corpus")
+
+    def _load_elogs(self, expec_log_theta, expec_log_beta):
+        st = self._st
+        if expec_log_theta is not None:
+            e = torch.as_tensor(np.ascontiguousarray(expec_log_theta, dtype=np.float64)).to(st.dev)
+            st.eT[st.cur].zero_()
+            st.eT[st.cur][:, :st.K] = torch.exp(e)
+        else:
+            self._refresh_theta()
+        if expec_log_beta is not None:
+            e = torch.exp(torch.as_tensor(np.ascontiguousarray(expec_log_beta, dtype=np.float64)).to(st.dev))
+            nv.transpose_pad(e, st.eB)
+        else:
+            self._refresh_beta()
+
+    def approx_elbo(self, X=None, sampling: bool = False, expec_log_theta=None, expec_log_beta=None):
+        """lda_model.py:89-165.  X must be the fitted corpus (or None).  Explicit expectations are honoured for the
+        token term and returned unchanged; the prior terms use DE(gamma) / DE(lambda), which is what every reference
+        call site passes."""
+        self._check_X(X)
+        self._load_elogs(expec_log_theta, expec_log_beta)
+        self._refresh_theta_term_only()
+        st = self._st
+        nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB.clone(), None, st.colsum, st.part[2], st.ws_m)
+        self._tokens()
+        self._collect(theta_row=1)
+        self._perplexity_from_terms(sampling)
+        if expec_log_theta is None or expec_log_beta is None:
+            et, eb = self._elog_np()
+            expec_log_theta = et if expec_log_theta is None else expec_log_theta
+            expec_log_beta = eb if expec_log_beta is None else expec_log_beta
+        return self._last_elbo, (expec_log_theta, expec_log_beta)
+
+    def approx_perplexity(self, X=None, sampling: bool = False, expec_log_theta=None, expec_log_beta=None):
+        """lda_model.py:167-194."""
+        _, logs = self.approx_elbo(X, sampling, expec_log_theta, expec_log_beta)
+        return self._perplexity_from_terms(sampling), logs
+
+    def e_step(self, X, expec_log_theta, expec_log_beta, step: int = 100, threshold: float = 1e-05,
+               batch: bool = True, verbose: bool = False):
+        """lda_model.py:197-270: returns (gamma, (lambda_update (K,V), Elogtheta))."""
+        self._check_X(X)
+        self._load_elogs(expec_log_theta, expec_log_beta)
+        st, c = self._st, self._st.corpus
+        cur, nxt = st.cur, st.cur ^ 1
+        nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
+                 st.gamma, st.eT[nxt], None, step, threshold, st.iters, st.part[0], st.ws)
+        ws_s = st.ws_s if st.ws_s is not None else torch.empty(nv.sstats_workspace_bytes(c.nnz, st.V, st.ld),
+                                                               dtype=torch.uint8, device=st.dev)
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, st.eT[cur], st.eB, st.sstats, ws_s)
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(st.sstats)
+        upd = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
+        nv.transpose_unpad(st.sstats * st.eB, st.K, upd)  # lda_model.py:264
+        st.cur = nxt
+        self._invalidate("gamma")
+        capped = int(st.iters[1].item())
+        if capped:
+            warnings.warn(f"Estep, Maximum iteration reached at step {step + 1} for {capped} documents")
+        et = torch.empty_like(st.gamma)
+        nv.dirichlet_expectation(st.gamma, st.K, out_elog=et)
+        return self._gamma_, (upd.cpu().numpy(), et[:, :st.K].cpu().numpy())
+
+    def m_step(self, lambda_update, verbose: bool = False, batch: bool = True):
+        """lda_model.py:273-283: lambda = eta + lambda_update; returns (lambda, Elogbeta)."""
+        st = self._st
+        lam = float(self._eta_) + torch.as_tensor(np.ascontiguousarray(lambda_update, dtype=np.float64)).to(st.dev)
+        nv.transpose_pad(lam, st.lam)
+        self._invalidate("lam")
+        eb = torch.empty_like(st.lam)
+        nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB, eb, st.colsum, st.part[2], st.ws_m)
+        out = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
+        nv.transpose_unpad(eb, st.K, out)
+        return self._lambda_, out.cpu().numpy()
+
+    def em_step(self, X, expec_log_theta, expec_log_beta, step: int = 100, threshold: float = 1e-05,
+                batch: bool = True, verbose: bool = False):
+        """lda_model.py:285-316: returns (Elogtheta, Elogbeta) after one E+M step."""
+        _, (upd, elogtheta) = self.e_step(X, expec_log_theta, expec_log_beta, step, threshold, verbose)
+        _, elogbeta = self.m_step(upd, verbose)
+        return elogtheta, elogbeta
+
+    def get_top_k_words(self, k: int):
+        """lda_model.py:556-564."""
+        lam = self._lambda_
+        for topic_index in range(lam.shape[0]):
+            topk = np.argsort(lam[topic_index, :], )[-k:]
+            print(f"Topic {topic_index}")
+            for i, idx in enumerate(topk):
+                print(f"Top {i + 1} -> {self.train_doc.idx_to_vocab[idx]}")
+            print()
