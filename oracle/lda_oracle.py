@@ -289,6 +289,7 @@ class OracleLDA:
                 _p(av, ctypes.c_double), self._alpha_sum(), float(self.eta), float(scale),
                 _p(parts, ctypes.c_double))
             self.last_parts = parts
+            self.last_elbo = float(elbo)
             return float(elbo), (Elogtheta, Elogbeta)
         elbo = 0
         for d in range(D):  # :125-139
@@ -303,6 +304,7 @@ class OracleLDA:
         if sampling:
             elbo = elbo * self.D_population / D
         elbo += self._prior_term_numpy(Elogbeta, self.eta, self.lam)  # :157-163
+        self.last_elbo = float(elbo)
         return float(elbo), (Elogtheta, Elogbeta)
 
     # -- lda_model.py:167-194 ------------------------------------------------------------------------------

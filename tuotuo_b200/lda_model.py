@@ -111,7 +111,7 @@ class LDASmoothed:
 
     def _upload_alpha(self):
         st = self._st
-        st.alpha_vec = torch.as_tensor(self._alpha_vec_host()).to(st.dev)
+        st.alpha_vec = torch.as_tensor(self._alpha_vec_host().copy()).to(st.dev)
 
     def _alloc_state(self, corpus: DeviceCorpus):
         dev = corpus.device
