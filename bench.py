@@ -5,10 +5,11 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
 
-A "step" is ONE full EM iteration of the hot path over the resident corpus: E-step (gamma + theta refresh),
-K x V sufficient statistics, [NCCL all-reduce of the statistics when N > 1], M-step (lambda + beta refresh), the
-ELBO token term and the device->host read of the perplexity terms — exactly what LDASmoothed.fit does per
-iteration.  Workload at N=1: BASELINE.json configs[2] "synthetic 1M docs x 300 tokens, K=100, V=50k" (cfg3), the
+A "step" is ONE full EM iteration of the hot path over the resident corpus: E-step (gamma + theta refresh, with the
+ELBO token term of the incoming state as a by-product of the same dot products), the device->host read of the
+perplexity terms and the host-side convergence test, K x V sufficient statistics, [NCCL all-reduce of the
+statistics when N > 1], M-step (lambda + beta refresh) — exactly the body of LDASmoothed.fit's loop; every step
+yields one perplexity.  Workload at N=1: BASELINE.json configs[2] "synthetic 1M docs x 300 tokens, K=100, V=50k" (cfg3), the
 configuration the 60 %-of-roofline target is quoted on; for N > 1 every rank holds its own cfg3-sized document
 shard (weak scaling), lambda is replicated and the statistics are summed with one fp64 all-reduce per iteration.
 
@@ -39,12 +40,12 @@ UNIT = "doc-tokens/s"
 def algorithmic_bytes(nnz, D, K, V):
     """Gather-model bytes.  Per launch of each kernel and per EM iteration."""
     kb = 8 * K
-    est = nnz * (kb + 8) + D * kb * 4 + (D + 1) * 8      # gather eB row + (colidx,count); eT in, gamma in/out, eT out
+    est = nnz * (kb + 8) + D * kb * 5 + (D + 1) * 8      # gather eB row + (colidx,count); eT in x2, gamma in/out, eT out
     sst = nnz * (kb + 8) + V * kb * 2 + (V + 1) * 8      # gather eT row + (docidx,count); eB in, S out
     mst = V * kb * 6                                       # S, eB in; lambda out; lambda in; eB out (+colsum pass)
-    elb = nnz * (kb + 8) + D * kb + (D + 1) * 8            # gather eB row + (colidx,count); eT in
+    # the ELBO token term is a by-product of the E-step (same dot product): no third gather => 16K bytes per nonzero
     return {"ttlda_estep_f64": est, "ttlda_sstats_csc_f64": sst, "ttlda_mstep_f64": mst,
-            "ttlda_elbo_tokens_f64": elb, "iteration": est + sst + mst + elb}
+            "iteration": est + sst + mst}
 
 
 def measured_peaks():
@@ -211,9 +212,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def one_step():
-        lda._em_iteration(e_num_step=100)
-        lda._collect(theta_row=0)
-        return lda._perplexity_from_terms(False)
+        # exactly the body of LDASmoothed.fit's loop: E-step (+ token term of the incoming state), 48-byte D2H and
+        # perplexity / convergence test on the host, statistics, [all-reduce], M-step
+        lda._estep_speculative(e_num_step=100)
+        lda._collect(tok_row=0)
+        p = lda._perplexity_from_terms(False)
+        st.part[1, 0].copy_(st.part[0, 1])
+        lda._commit_iteration()
+        return p
 
     perps = [float(p0[0])]
     for _ in range(args.warmup):
@@ -254,7 +260,7 @@ def run_ours(args):
         c.rowptr.copy_(h_rp, non_blocking=True)
         c.colidx.copy_(h_ci, non_blocking=True)
         c.counts.copy_(h_ct, non_blocking=True)
-        c.build_csc()
+        c.build_csc(c.nblocks, c.block_docs)
         return one_step()
 
     for _ in range(max(1, min(args.warmup, 2))):
@@ -307,7 +313,8 @@ def run_ours(args):
                                        f"({docs_all // world} docs per GPU), batch VI EM iteration",
                            "docs": docs_all, "doc_tokens": tokens_all, "nnz": nnz_all, "K": K, "V": V,
                            "parallelism": f"doc-shard x{world}" + (" + NCCL all-reduce(K*V f64)" if world > 1 else ""),
-                           "sstats": args.sstats,
+                           "sstats": args.sstats, "doc_blocks": c.nblocks,
+                           "elbo": "token term fused into the E-step (16K-byte-per-nonzero variant, SURVEY 8d)",
                            "l2": "no explicit flush: each step streams the CSR/CSC arrays and the D*K theta tables "
                                  f"({(c.nbytes() + 3 * c.D * K * 8) / 1e9:.1f} GB per GPU) >> 126 MB L2"},
                 "clocks": clocks, "gpu_launches": launches,

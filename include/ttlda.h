@@ -75,10 +75,13 @@ int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /* CSR -> CSC mirror (stable: documents ascending within each word).  No reference counterpart: the dense
- * matrix of tuotuo/document.py:36 is addressable both ways; the CSC copy gives the M-step the same access. */
-int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V);
+ * matrix of tuotuo/document.py:36 is addressable both ways; the CSC copy gives the M-step the same access.
+ * With nblocks > 1 the mirror is DOCUMENT-BLOCKED: documents are cut into nblocks blocks of block_docs documents
+ * and "virtual word" b*V + w lists the postings of word w inside block b (colptr has nblocks*V + 1 entries), so
+ * that the statistics pass gathers exp(E[log theta]) rows from one L2-sized window of the D x K table at a time. */
+int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int64_t nblocks);
 int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
-                     int64_t D, int64_t V, int64_t nnz,
+                     int64_t D, int64_t V, int64_t nnz, int64_t nblocks, int64_t block_docs,
                      int64_t* colptr, int32_t* docidx, int32_t* ccounts,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -107,6 +110,9 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
  * update is idempotent and the loop exits on its second pass; the kernel evaluates the update once and reports
  * `iters_out[0]` = sum over documents of the passes the reference would have made, `iters_out[1]` = documents
  * that hit the cap (`it > max_iter`, warned about at :258-259).
+ *   gamma_in: the previous gamma [D][ld]; read only for the loop statistics (may be NULL iff iters_out is NULL,
+ *   may alias gamma_out).  gamma_out / exp_elogtheta_out are written; exp_elogtheta_out must not alias the input
+ *   (ping-pong), which lets a caller run the pass speculatively and discard it.
  *   sstats_atomic: if non-NULL, also scatters sstats[w,k] += eT_in[d,k]*c/N with red.global.add.f64 (the
  *   one-pass alternative to ttlda_sstats_csc_f64; not bit-reproducible).  Must be zeroed by the caller.
  *   partial_out double[TTLDA_NPART]: [0] token term at the incoming state, [1] theta-prior term at the outgoing
@@ -116,7 +122,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     int64_t D, int64_t K, int64_t V, int64_t ld,
                     const double* alpha_vec, double alpha_sum,
                     const double* exp_elogtheta_in, const double* exp_elogbeta,
-                    double* gamma, double* exp_elogtheta_out, double* sstats_atomic,
+                    const double* gamma_in, double* gamma_out, double* exp_elogtheta_out, double* sstats_atomic,
                     int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -125,10 +131,12 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
  *      sstats[w,k] = sum_{d: X_dw>0} eT[d,k] * c_dw / (sum_k' eT[d,k'] eB[w,k'] + 1e-100)
  * Replaces: lambda_update[:, ids] += np.outer(eT, cts/phi_norm) at tuotuo/lda_model.py:262 (the trailing
  * `*= exp(Elogbeta)` of :264 is applied by ttlda_mstep_f64, after the cross-GPU sum — it is linear).
+ * colptr/docidx/ccounts: the (possibly document-blocked, nblocks >= 1) mirror built by ttlda_csr_to_csc; per-block
+ * partial statistics live in the workspace and are folded in block order; sstats [V][ld] is the total.
  */
-int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld);
+int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks);
 int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts,
-                         int64_t V, int64_t K, int64_t ld, int64_t nnz,
+                         int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks,
                          const double* exp_elogtheta, const double* exp_elogbeta, double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
 

@@ -122,6 +122,7 @@ def test_bow_to_csr_and_csc_bit_exact(golden_dir, nv, dev):
     tok = (rs.zipf(1.3, size=int(offs[-1])) % V).astype(np.int32)
     ref = CSRCorpus.from_token_ids(tok, offs, V)
     c = DeviceCorpus.from_token_ids(torch.as_tensor(tok).to(dev), torch.as_tensor(offs).to(dev), V)
+    c.build_csc()
     rp, ci, ct = c.host_csr()
     np.testing.assert_array_equal(rp, ref.rowptr)
     np.testing.assert_array_equal(ci, ref.colidx)
@@ -135,6 +136,18 @@ def test_bow_to_csr_and_csc_bit_exact(golden_dir, nv, dev):
     np.testing.assert_array_equal(c.colptr.cpu().numpy(), m.indptr)
     np.testing.assert_array_equal(c.docidx.cpu().numpy()[:c.nnz], m.indices)
     np.testing.assert_array_equal(c.ccounts.cpu().numpy()[:c.nnz], m.data)
+    # document-blocked mirror: virtual word b*V + w lists the postings of w inside document block b
+    nb, bd = 4, 53
+    c.build_csc(nb, bd)
+    cp, di, cc = c.colptr.cpu().numpy(), c.docidx.cpu().numpy()[:c.nnz], c.ccounts.cpu().numpy()[:c.nnz]
+    assert len(cp) == nb * V + 1 and cp[0] == 0 and cp[-1] == c.nnz
+    full = sp.csr_matrix((ref.counts, ref.colidx, ref.rowptr), shape=(D, V))
+    for b in range(nb):
+        blk = full[b * bd:min(D, (b + 1) * bd)].tocsc()
+        blk.sort_indices()
+        np.testing.assert_array_equal(np.diff(cp[b * V:(b + 1) * V + 1]), np.diff(blk.indptr))
+        np.testing.assert_array_equal(di[cp[b * V]:cp[(b + 1) * V]], blk.indices + b * bd)
+        np.testing.assert_array_equal(cc[cp[b * V]:cp[(b + 1) * V]], blk.data)
     # golden: the reference's Document on the README corpus
     j = json.load(open(os.path.join(golden_dir, "cfg1_docs.json")))
     from tuotuo.document import Document
@@ -146,15 +159,17 @@ def test_bow_to_csr_and_csc_bit_exact(golden_dir, nv, dev):
     # empty corpus
     e = DeviceCorpus.from_token_ids(torch.zeros(0, dtype=torch.int32, device=dev),
                                     torch.zeros(4, dtype=torch.int64, device=dev), 9)
+    e.build_csc()
     assert e.nnz == 0 and e.rowptr.cpu().tolist() == [0, 0, 0, 0] and e.colptr.cpu().tolist() == [0] * 10
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode):
+def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1):
     """theta/beta refresh -> estep -> sstats -> mstep -> tokens, all through the C ABI; returns host results."""
     from tuotuo_b200.corpus import DeviceCorpus
 
     c = DeviceCorpus.from_host_csr(X.rowptr, X.colidx, X.counts, X.V, dev)
+    c.build_csc(nblocks)
     ld = nv.ld_for(K)
     D, V = X.D, X.V
     gamma = dpad(gamma0, ld, dev)
@@ -170,7 +185,7 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode):
     iters = torch.zeros(2, dtype=torch.int64, device=dev)
     ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
     ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
-    ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, V, ld), dtype=torch.uint8, device=dev)
+    ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, V, ld, c.nblocks), dtype=torch.uint8, device=dev)
     av = torch.as_tensor(np.ascontiguousarray(np.broadcast_to(np.asarray(alpha, dtype=np.float64).reshape(-1), (K,)))).to(dev)
     asum = float(np.sum(alpha))
     nv.theta_refresh(gamma, K, av, asum, eT0, part[0], ws)
@@ -178,10 +193,10 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode):
     nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, eT0, eB, part[2], ws)
     elbo0 = float(part[0, 0] + part[1, 0] + part[2, 0])
     if mode == "atomic":
-        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, eT1, S, 100, 1e-5, iters, part[3], ws)
+        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, S, 100, 1e-5, iters, part[3], ws)
     else:
-        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, eT1, None, 100, 1e-5, iters, part[3], ws)
-        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, eT0, eB, S, ws_s)
+        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, None, 100, 1e-5, iters, part[3], ws)
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, c.nblocks, eT0, eB, S, ws_s)
     upd = torch.empty((K, V), dtype=torch.float64, device=dev)
     nv.transpose_unpad(S * eB, K, upd)
     elog_b = torch.zeros_like(lam)
@@ -198,11 +213,11 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode):
                     gamma[:, K:].abs().sum() + eT1[:, K:].abs().sum() + lam_new[:, K:].abs().sum() + eB[:, K:].abs().sum()))
 
 
-@pytest.mark.parametrize("mode", ["csc", "atomic"])
-def test_single_em_step_vs_reference(golden_dir, nv, dev, mode):
+@pytest.mark.parametrize("mode,nblocks", [("csc", 1), ("csc", 3), ("csc", 200), ("atomic", 1)])
+def test_single_em_step_vs_reference(golden_dir, nv, dev, mode, nblocks):
     g = _load(golden_dir, "estep_small.npz")
     X = CSRCorpus(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
-    r = _single_step(nv, dev, X, int(g["K"]), g["gamma0"], g["lam0"], 1, mode)
+    r = _single_step(nv, dev, X, int(g["K"]), g["gamma0"], g["lam0"], 1, mode, nblocks)
     assert relerr(r["elbo0"], g["elbo0"]) < 1e-12
     assert relerr(r["gamma"], g["gamma1"]) < TOL_STATE
     assert relerr(r["sstats"], g["sstats1"]) < TOL_STATE
@@ -347,12 +362,48 @@ def test_invariants_at_scale(nv, dev):
     perps = m.fit(doc, em_num_step=3, update_hyper_parms=False, return_perplexities=True)
     st = m._st
     c = st.corpus
-    assert c.tokens == 200_000 * 300
+    assert c.tokens == 200_000 * 300 and c.nblocks > 1  # 160 MB of theta rows => document-blocked statistics pass
     lens = torch.zeros(c.D, dtype=torch.float64, device=dev)
     rows = torch.repeat_interleave(torch.arange(c.D, device=dev), torch.diff(c.rowptr))
     lens.index_add_(0, rows, c.counts.to(torch.float64))
-    assert float(((st.gamma[:, :100].sum(1) - 100.0) - lens).abs().max()) < 1e-9
+    assert float(((st.gamma[st.cur][:, :100].sum(1) - 100.0) - lens).abs().max()) < 1e-9
     tot = float((st.lam[:, :100] - 1.0).sum())  # lambda - eta = sstats * eB
     assert abs(tot - c.tokens) / c.tokens < 1e-12
     assert perps[0] > perps[1] > perps[2] > perps[3]
     assert st.terms["count"] == c.tokens
+
+
+def test_blocked_and_unblocked_statistics_agree(monkeypatch):
+    """The document-blocked CSC mirror only reorders the (fixed-order) summation: results agree to rounding."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(21, 700, 900, 20, 60, ragged=True)
+    res = {}
+    for nb in ("1", "7"):
+        monkeypatch.setenv("TTLDA_DOC_BLOCKS", nb)
+        doc = Document.from_csr(rp, ci, ct, 900)
+        m = LDASmoothed(50, verbose=False)
+        p = m.fit(doc, em_num_step=3, return_perplexities=True)
+        assert m._st.corpus.nblocks == int(nb)
+        res[nb] = (p, m._lambda_.copy(), m._gamma_.copy())
+    assert relerr(res["1"][0], res["7"][0]) < 1e-13
+    assert relerr(res["1"][1], res["7"][1]) < 1e-12 and relerr(res["1"][2], res["7"][2]) < 1e-12
+
+
+@pytest.mark.parametrize("G", ["2", "4", "8", "16", "32"])
+def test_every_group_width_is_exact(monkeypatch, G):
+    """TTLDA_GROUP forces the lanes-per-K-vector mapping; every width must give the same answer as the oracle."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    K, V = 30, 500  # ld = 32: representable with every G (E = 8, 4, 2, 1, 1)
+    rp, ci, ct = numpy_corpus(33, 150, V, 12, 45, ragged=True)
+    o = OracleLDA(K, engine="c")
+    po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=2)
+    monkeypatch.setenv("TTLDA_GROUP", G)
+    m = LDASmoothed(K, verbose=False)
+    pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, return_perplexities=True)
+    assert relerr(pg, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE

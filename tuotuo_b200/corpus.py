@@ -16,7 +16,10 @@ from . import _native as nv
 class DeviceCorpus:
     """rowptr int64[D+1], colidx int32[nnz] (ascending per row), counts int32[nnz] and the CSC mirror, on one device."""
 
-    def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = True):
+    L2_WINDOW_BYTES = 48 << 20   # exp(E[log theta]) rows one document block may occupy (126 MB L2 on B200)
+    MAX_BLOCK_BYTES = 2 << 30    # cap on the per-block statistics buffer nblocks * V * ld * 8
+
+    def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = False):
         assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and counts.dtype == torch.int32
         self.rowptr, self.colidx, self.counts = rowptr.contiguous(), colidx.contiguous(), counts.contiguous()
         self.device = rowptr.device
@@ -25,6 +28,7 @@ class DeviceCorpus:
         self.nnz = int(colidx.numel())
         self.tokens = int(counts.sum(dtype=torch.int64).item()) if self.nnz else 0
         self.colptr = self.docidx = self.ccounts = None
+        self.nblocks, self.block_docs = 0, 0
         if build_csc:
             self.build_csc()
 
@@ -51,15 +55,45 @@ class DeviceCorpus:
         del ws
         return DeviceCorpus(rowptr, colidx[:nnz].clone(), counts[:nnz].clone(), V, **kw)
 
-    def build_csc(self):
+    def plan_blocks(self, ld: int):
+        """Document blocking of the CSC mirror for K-vector rows of `ld` doubles: blocks whose exp(E[log theta])
+        rows fit an L2-sized window, if that needs few enough blocks to keep the per-block statistics small."""
+        import os
+
+        ov = os.environ.get("TTLDA_DOC_BLOCKS")
+        if ov:
+            nb = max(1, int(ov))
+        else:
+            row = ld * 8
+            nb = max(1, -(-self.D * row // self.L2_WINDOW_BYTES))
+            if nb > 1 and nb * self.V * row > self.MAX_BLOCK_BYTES:
+                nb = 1  # the window cannot be made L2-sized within the memory cap: stay unblocked (HBM gather)
+        nb = min(nb, max(1, self.D))
+        block_docs = max(1, -(-self.D // nb))
+        nb = max(1, -(-self.D // block_docs))
+        return nb, block_docs
+
+    def build_csc(self, nblocks: int = 1, block_docs: int | None = None):
+        """(Re)build the CSC mirror on the device; document-blocked when nblocks > 1 (ttlda_csr_to_csc)."""
         dev = self.device
-        ws = torch.empty(nv.csr_to_csc_workspace_bytes(self.nnz, self.D, self.V), dtype=torch.uint8, device=dev)
-        self.colptr = torch.empty(self.V + 1, dtype=torch.int64, device=dev)
-        self.docidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
-        self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
-        nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, self.colptr, self.docidx,
-                      self.ccounts, ws)
+        nblocks = max(1, int(nblocks))
+        block_docs = int(block_docs) if block_docs else max(1, -(-self.D // nblocks))
+        ws = torch.empty(nv.csr_to_csc_workspace_bytes(self.nnz, self.D, self.V, nblocks), dtype=torch.uint8,
+                         device=dev)
+        if self.colptr is None or self.colptr.numel() != nblocks * self.V + 1:
+            self.colptr = torch.empty(nblocks * self.V + 1, dtype=torch.int64, device=dev)
+        if self.docidx is None:
+            self.docidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
+                      self.colptr, self.docidx, self.ccounts, ws)
+        self.nblocks, self.block_docs = nblocks, block_docs
         del ws
+
+    def ensure_csc(self, ld: int):
+        nb, bd = self.plan_blocks(ld)
+        if self.colptr is None or (self.nblocks, self.block_docs) != (nb, bd):
+            self.build_csc(nb, bd)
 
     # -- host views ----------------------------------------------------------------------------------------------------
     def host_csr(self):

@@ -52,30 +52,38 @@ __global__ void split_runs_kernel(const uint64_t* __restrict__ ukeys, const int6
     }
 }
 
-__global__ void iota_u32_kernel(uint32_t* __restrict__ v, int64_t n)
+// key of CSR position p = (doc(p) / block_docs) * V + word(p); doc(p) by binary search in rowptr (empty documents are
+// skipped correctly).  Also materialises doc(p) and the identity permutation for the pair sort.
+__global__ void csc_keys_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t D,
+                                int64_t V, int64_t nnz, int64_t block_docs, uint32_t* __restrict__ keys,
+                                uint32_t* __restrict__ docs, uint32_t* __restrict__ pos)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        v[i] = (uint32_t)i;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = D;  // last d with rowptr[d] <= p
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rowptr[mid] <= p) lo = mid; else hi = mid;
+        }
+        keys[p] = (uint32_t)((lo / block_docs) * V + colidx[p]);
+        docs[p] = (uint32_t)lo;
+        pos[p] = (uint32_t)p;
+    }
 }
 
-// after the stable sort by word: gather doc id (binary search in rowptr) and count of each CSR position; build colptr
+// after the stable sort by (block, word): gather doc id and count of each CSR position; build colptr over the
+// VV = nblocks * V virtual words
 __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ spos,
-                                  const int64_t* __restrict__ rowptr, const int32_t* __restrict__ counts, int64_t D,
-                                  int64_t V, int64_t nnz, int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
+                                  const uint32_t* __restrict__ docs, const int32_t* __restrict__ counts, int64_t VV,
+                                  int64_t nnz, int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
                                   int32_t* __restrict__ ccounts)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t wcur = (i < nnz) ? (int64_t)skeys[i] : V;
+        const int64_t wcur = (i < nnz) ? (int64_t)skeys[i] : VV;
         const int64_t wprev = (i > 0) ? (int64_t)skeys[i - 1] : -1;
         for (int64_t w = wprev + 1; w <= wcur; ++w) colptr[w] = i;
         if (i < nnz) {
             const int64_t p = spos[i];
-            int64_t lo = 0, hi = D;  // last d with rowptr[d] <= p  (skips empty documents correctly)
-            while (hi - lo > 1) {
-                const int64_t mid = (lo + hi) >> 1;
-                if (rowptr[mid] <= p) lo = mid; else hi = mid;
-            }
-            docidx[i] = (int32_t)lo;
+            docidx[i] = (int32_t)docs[p];
             ccounts[i] = counts[p];
         }
     }
@@ -110,18 +118,20 @@ static cudaError_t bow_layout(int64_t T, int64_t D, int64_t V, char* base, BowWs
 }
 
 struct CscWs {
-    uint32_t *skeys, *pos, *spos;
+    uint32_t *keys, *docs, *skeys, *pos, *spos;
     void* cub;
     size_t cub_bytes, total;
 };
 
-static cudaError_t csc_layout(int64_t nnz, int64_t V, char* base, CscWs& w)
+static cudaError_t csc_layout(int64_t nnz, int64_t VV, char* base, CscWs& w)
 {
     size_t sort_b = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, sort_b, (uint32_t*)nullptr, (uint32_t*)nullptr,
-                                                    (uint32_t*)nullptr, (uint32_t*)nullptr, nnz, 0, bits_for(V));
+                                                    (uint32_t*)nullptr, (uint32_t*)nullptr, nnz, 0, bits_for(VV));
     if (e != cudaSuccess) return e;
     size_t off = 0;
+    w.keys = (uint32_t*)(base + off);  off += align256((size_t)nnz * 4);
+    w.docs = (uint32_t*)(base + off);  off += align256((size_t)nnz * 4);
     w.skeys = (uint32_t*)(base + off); off += align256((size_t)nnz * 4);
     w.pos = (uint32_t*)(base + off);   off += align256((size_t)nnz * 4);
     w.spos = (uint32_t*)(base + off);  off += align256((size_t)nnz * 4);
@@ -188,41 +198,43 @@ int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64
     return TTLDA_OK;
 }
 
-int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V)
+int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int64_t nblocks)
 {
     (void)D;
-    if (nnz < 0 || V < 0) return TTLDA_EINVAL;
+    if (nnz < 0 || V < 0 || nblocks < 1) return TTLDA_EINVAL;
     CscWs w;
-    cudaError_t e = csc_layout(nnz, V, nullptr, w);
+    cudaError_t e = csc_layout(nnz, nblocks * V, nullptr, w);
     if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc workspace query");
     return (int64_t)w.total;
 }
 
 int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
-                     int64_t nnz, int64_t* colptr, int32_t* docidx, int32_t* ccounts, void* workspace,
-                     int64_t workspace_bytes, void* stream)
+                     int64_t nnz, int64_t nblocks, int64_t block_docs, int64_t* colptr, int32_t* docidx,
+                     int32_t* ccounts, void* workspace, int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(rowptr && colptr && workspace, "NULL pointer");
     TTLDA_REQUIRE(nnz == 0 || (colidx && counts && docidx && ccounts), "NULL pointer");
     TTLDA_REQUIRE(nnz >= 0 && D >= 0 && V >= 0, "negative size");
     TTLDA_REQUIRE(nnz < ((int64_t)1 << 32), "nnz per device must be < 2^32");
+    TTLDA_REQUIRE(nblocks >= 1 && block_docs >= 1 && nblocks * block_docs >= D, "document blocks must cover D");
+    TTLDA_REQUIRE(nblocks * V < ((int64_t)1 << 31), "nblocks * V must be < 2^31");
     cudaStream_t s = (cudaStream_t)stream;
+    const int64_t VV = nblocks * V;
     CscWs w;
-    cudaError_t e = csc_layout(nnz, V, (char*)workspace, w);
+    cudaError_t e = csc_layout(nnz, VV, (char*)workspace, w);
     if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc layout");
     if ((int64_t)w.total > workspace_bytes) {
         set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
         return TTLDA_EWORKSPACE;
     }
     if (nnz > 0) {
-        iota_u32_kernel<<<grid_1d(nnz), 256, 0, s>>>(w.pos, nnz);
-        TTLDA_LAUNCH_CHECK("iota");
-        // LSD radix sort is stable: within a word, CSR positions (hence documents) stay ascending.
-        e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, reinterpret_cast<const uint32_t*>(colidx), w.skeys,
-                                            w.pos, w.spos, nnz, 0, bits_for(V), s);
+        csc_keys_kernel<<<grid_1d(nnz), 256, 0, s>>>(rowptr, colidx, D, V, nnz, block_docs, w.keys, w.docs, w.pos);
+        TTLDA_LAUNCH_CHECK("csc_keys");
+        // LSD radix sort is stable: within a (block, word), CSR positions (hence documents) stay ascending.
+        e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, w.keys, w.skeys, w.pos, w.spos, nnz, 0, bits_for(VV), s);
         if (e != cudaSuccess) return cuda_fail(e, "radix sort (csc)");
     }
-    csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, rowptr, counts, D, V, nnz, colptr, docidx,
+    csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, w.docs, counts, VV, nnz, colptr, docidx,
                                                        ccounts);
     TTLDA_LAUNCH_CHECK("csc_gather");
     return TTLDA_OK;

@@ -4,16 +4,19 @@
 // Reference: LDASmoothed.e_step tuotuo/lda_model.py:197-270; approx_elbo token loop :125-139; theta-prior term
 // :25-46,:142-148; Dirichlet expectation tuotuo/cutils.pyx:41-93.
 //
-// Mapping: ONE WARP PER DOCUMENT, the K topics live in registers: lane l owns the double2 slices
-// k = 2l + 64j (+0,+1), j < KP, so that one warp-wide 16-byte load covers 512 contiguous bytes of a word's
-// K-vector in the word-major exp(E[log beta]) table [V][ld].  Per nonzero (w, c):
-//     p = sum_k eT_k * eB[w,k]            (2*KP DFMA per lane + butterfly)
+// Mapping (traverse.cuh): one WARP per document, the document's exp(E[log theta_d]) K-vector lives in registers,
+// replicated over the warp's R = 32/G lane groups; each group gathers the exp(E[log beta_w]) K-vector of a
+// different nonzero of the document from the word-major [V][ld] table, so R nonzeros advance per instruction:
+//     p = sum_k eT_k * eB[w,k]            (2E DFMA per lane + log2(G) shuffle steps)
 //     r = c / (p + 1e-100)                (lda_model.py:242)
-//     acc_k += r * eB[w,k]                (lda_model.py:248, the (cts/norm) . eB^T product)
-// and, after the row, gamma_k = alpha_k + eT_k * acc_k.  The CSR (word, count) pairs are fetched 32 at a time
-// (one coalesced load per lane) and broadcast with shuffles; the next word's K-vector is prefetched into
-// registers while the current one is consumed.  Bound: HBM/L2 gather of 8K bytes per nonzero.
-#include "ttlda_common.cuh"
+//     acc_k += r * eB[w,k]                (lda_model.py:248, the (cts/norm) . eB^T product; per-group partials)
+// The (word, count) pairs are fetched 32 at a time (one coalesced load per lane) and routed to the groups by
+// shuffle; the next sub-batch's K-vectors are prefetched into registers.  p of every nonzero is handed back to
+// the lane that loaded it, so the token term costs ONE log per nonzero per lane.  Per-document epilogue: group
+// partials are transposed through shared memory to a 32-lane layout (k = lane + 32m), then
+// gamma_k = alpha_k + eT_k * acc_k, AS-103 psi, exp, lgamma => new exp(E[log theta_d]) and the theta-prior term.
+// Bound: gather of 8K bytes per nonzero (L2 when the 8*K*V-byte table fits, else HBM).
+#include "traverse.cuh"
 
 namespace ttlda {
 
@@ -28,7 +31,8 @@ struct EStepParams {
     double alpha_sum;
     const double* eT_in;
     const double* eB;
-    double* gamma;
+    const double* gamma_in;  // previous gamma (only read for the loop statistics), may be NULL
+    double* gamma_out;
     double* eT_out;
     double* sstats_atomic;
     int64_t max_iter;
@@ -37,33 +41,20 @@ struct EStepParams {
     double* records;
 };
 
-template <int KP>
-__device__ __forceinline__ void load_row(double2 (&v)[KP], const double* __restrict__ row, int lane, int ld)
-{
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        const int k = 2 * lane + 64 * j;
-        v[j] = (k < ld) ? ldg2(row + k) : make_double2(0., 0.);
-    }
-}
+constexpr int kDocThreads = 128;  // 4 warps per CTA
 
-template <int KP>
-__device__ __forceinline__ double dot_row(const double2 (&t)[KP], const double2 (&b)[KP])
+template <int G, int E, bool PREFETCH, bool ESTEP>
+__global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams P)
 {
-    double p = 0.;
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        p = fma(t[j].x, b[j].x, p);
-        p = fma(t[j].y, b[j].y, p);
-    }
-    return warp_sum(p);
-}
+    constexpr int R = 32 / G;
+    constexpr int LDP = 2 * G * E;
+    constexpr int MMAX = (LDP + 31) / 32;
+    extern __shared__ double smem[];
+    double* red = smem;  // 3*32 doubles for the CTA reduction
+    double* wbuf = smem + 96 + (threadIdx.x >> 5) * (R * LDP);
 
-template <int KP, bool PREFETCH, bool ESTEP>
-__global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
-{
-    __shared__ double sm[3 * 32];
     const int lane = threadIdx.x & 31;
+    const int g = lane % G, r = lane / G;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld, K = P.K;
@@ -79,10 +70,9 @@ __global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
 
     for (int64_t d = warp0; d < P.D; d += nwarps) {
         const int64_t b = P.rowptr[d], e = P.rowptr[d + 1];
-        double2 t[KP], acc[KP];
-        load_row<KP>(t, P.eT_in + d * P.ld, lane, ld);
-#pragma unroll
-        for (int j = 0; j < KP; ++j) acc[j] = make_double2(0., 0.);
+        KSlice<G, E> t, acc;
+        t.load(P.eT_in + d * P.ld, g, ld);
+        acc.zero();
 
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
@@ -92,72 +82,64 @@ __global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
                 my_c = ld_stream_s32(P.counts + n0 + lane);
             }
             double my_p = 1.;
-            double2 cur[KP], nxt[KP];
-            {
-                const int w = __shfl_sync(0xffffffffu, my_w, 0);
-                load_row<KP>(cur, P.eB + (int64_t)w * P.ld, lane, ld);
-            }
-            for (int i = 0; i < cnt; ++i) {
-                if (PREFETCH && i + 1 < cnt) {
-                    const int wn = __shfl_sync(0xffffffffu, my_w, i + 1);
-                    load_row<KP>(nxt, P.eB + (int64_t)wn * P.ld, lane, ld);
-                }
-                const int w = __shfl_sync(0xffffffffu, my_w, i);
-                const int c = __shfl_sync(0xffffffffu, my_c, i);
-                const double p = dot_row<KP>(t, cur);
-                if (lane == i) my_p = p;
+            const int nsub = (cnt + R - 1) / R;
+            KSlice<G, E> cur, nxt;
+            cur.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, r) * P.ld, g, ld);
+            for (int s = 0; s < nsub; ++s) {
+                const int i = s * R + r;  // nonzero handled by this group in this sub-batch
+                if (PREFETCH && s + 1 < nsub)
+                    nxt.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, i + R) * P.ld, g, ld);
+                const int c = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt: the group idles harmlessly
+                const int wi = __shfl_sync(0xffffffffu, my_w, i);
+                const double p = group_sum<G>(t.dot(cur));
                 if (ESTEP) {
-                    const double r = (double)c / (p + 1e-100);
+                    const double rr = (double)c / (p + 1e-100);
+                    acc.axpy(rr, cur);
+                    if (P.sstats_atomic && c) {
+                        double* srow = P.sstats_atomic + (int64_t)wi * P.ld;
 #pragma unroll
-                    for (int j = 0; j < KP; ++j) {
-                        acc[j].x = fma(r, cur[j].x, acc[j].x);
-                        acc[j].y = fma(r, cur[j].y, acc[j].y);
-                    }
-                    if (P.sstats_atomic) {
-                        double* srow = P.sstats_atomic + (int64_t)w * P.ld;
-#pragma unroll
-                        for (int j = 0; j < KP; ++j) {
-                            const int k = 2 * lane + 64 * j;
-                            if (k < K) atomicAdd(srow + k, t[j].x * r);
-                            if (k + 1 < K) atomicAdd(srow + k + 1, t[j].y * r);
+                        for (int j = 0; j < E; ++j) {
+                            const int k = 2 * (g + G * j);
+                            if (k < K) atomicAdd(srow + k, t.v[j].x * rr);
+                            if (k + 1 < K) atomicAdd(srow + k + 1, t.v[j].y * rr);
                         }
                     }
                 }
+                // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
+                const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
+                if (lane / R == s) my_p = pv;
                 if (PREFETCH) {
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) cur[j] = nxt[j];
-                } else if (i + 1 < cnt) {
-                    const int wn = __shfl_sync(0xffffffffu, my_w, i + 1);
-                    load_row<KP>(cur, P.eB + (int64_t)wn * P.ld, lane, ld);
+                    cur = nxt;
+                } else if (s + 1 < nsub) {
+                    cur.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, i + R) * P.ld, g, ld);
                 }
             }
-            // one log per nonzero, evaluated by the lane that owns it
-            if (lane < cnt) {
+            if (lane < cnt) {  // one log per nonzero
                 tok_acc += (double)my_c * log(my_p);
                 cnt_acc += (double)my_c;
             }
         }
 
         if (ESTEP) {
-            // gamma_k = alpha_k + eT_k * acc_k  (lda_model.py:248), then theta refresh + theta-prior term
-            double* g = P.gamma + d * P.ld;
-            double2 gn[KP];
+            // group partials -> 32-lane layout through shared memory
+            acc.to_smem(wbuf + r * LDP, g);
+            __syncwarp();
+            double gn[MMAX];
             double s = 0., l1 = 0.;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const int k = 2 * lane + 64 * j;
-                gn[j] = make_double2(0., 0.);
+            for (int m = 0; m < MMAX; ++m) {
+                const int k = lane + 32 * m;
+                gn[m] = 0.;
                 if (k < K) {
-                    gn[j].x = P.alpha_vec[k] + t[j].x * acc[j].x;
-                    s += gn[j].x;
-                    if (P.iters) l1 += fabs(gn[j].x - g[k]);
-                }
-                if (k + 1 < K) {
-                    gn[j].y = P.alpha_vec[k + 1] + t[j].y * acc[j].y;
-                    s += gn[j].y;
-                    if (P.iters) l1 += fabs(gn[j].y - g[k + 1]);
+                    double a = 0.;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
+                    gn[m] = P.alpha_vec[k] + P.eT_in[d * P.ld + k] * a;  // lda_model.py:248
+                    s += gn[m];
+                    if (P.iters) l1 += fabs(gn[m] - P.gamma_in[d * P.ld + k]);
                 }
             }
+            __syncwarp();
             s = warp_sum(s);
             if (P.iters) {
                 l1 = warp_sum(l1);
@@ -170,23 +152,18 @@ __global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
             const double pt = psi_as103(s);
             double th = 0.;
 #pragma unroll
-            for (int j = 0; j < KP; ++j) {
-                const int k = 2 * lane + 64 * j;
-                double2 et = make_double2(0., 0.);
+            for (int m = 0; m < MMAX; ++m) {
+                const int k = lane + 32 * m;
                 if (k < K) {
-                    const double el = psi_as103(gn[j].x) - pt;
-                    th += (P.alpha_vec[k] - gn[j].x) * el + lgamma(gn[j].x);
-                    et.x = exp(el);
+                    const double el = psi_as103(gn[m]) - pt;
+                    th += (P.alpha_vec[k] - gn[m]) * el + lgamma(gn[m]);
+                    P.gamma_out[d * P.ld + k] = gn[m];
+                    P.eT_out[d * P.ld + k] = exp(el);
                 }
-                if (k + 1 < K) {
-                    const double el = psi_as103(gn[j].y) - pt;
-                    th += (P.alpha_vec[k + 1] - gn[j].y) * el + lgamma(gn[j].y);
-                    et.y = exp(el);
-                }
-                if (k < ld) {
-                    *reinterpret_cast<double2*>(g + k) = gn[j];
-                    *reinterpret_cast<double2*>(P.eT_out + d * P.ld + k) = et;
-                }
+            }
+            if (lane < ld - K) {  // padding columns
+                P.gamma_out[d * P.ld + K + lane] = 0.;
+                P.eT_out[d * P.ld + K + lane] = 0.;
             }
             th = warp_sum(th);
             theta_acc += th - lga + (lg_asum - lgamma(s));
@@ -194,7 +171,7 @@ __global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
     }
 
     double v[3] = {tok_acc, (lane == 0) ? theta_acc : 0., cnt_acc};
-    block_sum<3>(v, sm);
+    block_sum<3>(v, red);
     if (threadIdx.x == 0) {
         double* rec = P.records + (size_t)blockIdx.x * NPART;
         rec[0] = v[0];
@@ -209,25 +186,33 @@ __global__ void __launch_bounds__(256) doc_pass_kernel(const EStepParams P)
     }
 }
 
-template <bool ESTEP>
-static int launch_doc_pass(const EStepParams& P, int grid, cudaStream_t s)
+template <int G, int E, bool ESTEP>
+static int launch_shape(const EStepParams& P, int grid, cudaStream_t s)
 {
-    const int need = (int)((P.ld + 63) / 64);
-#define TTLDA_CASE(KP, PF)                                            \
-    if (need <= KP) {                                                 \
-        doc_pass_kernel<KP, PF, ESTEP><<<grid, 256, 0, s>>>(P);        \
-        return TTLDA_OK;                                              \
+    constexpr int R = 32 / G;
+    constexpr size_t smem = (96 + (kDocThreads / 32) * R * 2 * G * E) * sizeof(double);
+    constexpr bool PF = (E <= 8);  // register budget: t, acc, cur, nxt = 8E doubles
+    doc_pass_kernel<G, E, PF, ESTEP><<<grid, kDocThreads, smem, s>>>(P);
+    return TTLDA_OK;
+}
+
+template <bool ESTEP>
+static int launch_doc_pass(const EStepParams& P, cudaStream_t s)
+{
+    GroupShape gs = group_shape_for(P.ld);
+    if (const char* ov = getenv("TTLDA_GROUP")) {  // tuning override: lanes per K-vector
+        const int G = atoi(ov);
+        if (G == 2 || G == 4 || G == 8 || G == 16 || G == 32) {
+            const int E = (int)((P.ld + 2 * G - 1) / (2 * G));
+            gs = {G, E};
+        }
     }
-    TTLDA_CASE(1, true)
-    TTLDA_CASE(2, true)
-    TTLDA_CASE(3, true)
-    TTLDA_CASE(4, true)
-    TTLDA_CASE(6, false)
-    TTLDA_CASE(8, false)
-    TTLDA_CASE(12, false)
-    TTLDA_CASE(16, false)
+    const int grid = grid_for_warps(P.D, kDocThreads / 32, 16);
+#define TTLDA_CASE(GG, EE) \
+    if (gs.G == GG && gs.E == EE) return launch_shape<GG, EE, ESTEP>(P, grid, s);
+    TTLDA_FOR_EACH_SHAPE(TTLDA_CASE)
 #undef TTLDA_CASE
-    set_error("K too large (ld=%lld > %d)", (long long)P.ld, TTLDA_MAX_K);
+    set_error("no kernel instantiated for ld=%lld (G=%d, E=%d)", (long long)P.ld, gs.G, gs.E);
     return TTLDA_EINVAL;
 }
 
@@ -239,17 +224,18 @@ extern "C" {
 
 int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t K,
                     int64_t V, int64_t ld, const double* alpha_vec, double alpha_sum,
-                    const double* exp_elogtheta_in, const double* exp_elogbeta, double* gamma,
-                    double* exp_elogtheta_out, double* sstats_atomic, int64_t max_iter, double tol,
+                    const double* exp_elogtheta_in, const double* exp_elogbeta, const double* gamma_in,
+                    double* gamma_out, double* exp_elogtheta_out, double* sstats_atomic, int64_t max_iter, double tol,
                     int64_t* iters_out, double* partial_out, void* workspace, int64_t workspace_bytes, void* stream)
 {
-    TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma && exp_elogtheta_out &&
+    TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma_out && exp_elogtheta_out &&
                       partial_out && workspace,
                   "NULL pointer");
     TTLDA_REQUIRE(D >= 0 && V >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
-    TTLDA_REQUIRE(ld >= K && ld % 4 == 0, "ld must be a multiple of 4 and >= K");
+    TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
     TTLDA_REQUIRE(exp_elogtheta_in != exp_elogtheta_out, "exp_elogtheta_out must not alias the input");
     TTLDA_REQUIRE(max_iter >= 0, "max_iter must be >= 0");
+    TTLDA_REQUIRE(!iters_out || gamma_in, "iters_out needs gamma_in (the previous gamma)");
     if (workspace_bytes < reduce_ws_bytes()) {
         set_error("estep: workspace %lld < %lld", (long long)workspace_bytes, (long long)reduce_ws_bytes());
         return TTLDA_EWORKSPACE;
@@ -260,13 +246,12 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
         if (e != cudaSuccess) return cuda_fail(e, "memset iters");
     }
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta_in, exp_elogbeta,
-                  gamma, exp_elogtheta_out, sstats_atomic, max_iter, tol, (unsigned long long*)iters_out,
-                  (double*)workspace};
-    const int grid = grid_for_warps(D, 8, 8);
-    int rc = launch_doc_pass<true>(P, grid, s);
+                  gamma_in, gamma_out, exp_elogtheta_out, sstats_atomic, max_iter, tol,
+                  (unsigned long long*)iters_out, (double*)workspace};
+    int rc = launch_doc_pass<true>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("estep");
-    return launch_reduce_records((const double*)workspace, grid, partial_out, s);
+    return launch_reduce_records((const double*)workspace, grid_for_warps(D, kDocThreads / 32, 16), partial_out, s);
 }
 
 int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t K,
@@ -275,19 +260,18 @@ int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const in
 {
     TTLDA_REQUIRE(rowptr && exp_elogtheta && exp_elogbeta && partial_out && workspace, "NULL pointer");
     TTLDA_REQUIRE(D >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
-    TTLDA_REQUIRE(ld >= K && ld % 4 == 0, "ld must be a multiple of 4 and >= K");
+    TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
     if (workspace_bytes < reduce_ws_bytes()) {
         set_error("elbo_tokens: workspace too small");
         return TTLDA_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, nullptr, 0., exp_elogtheta, exp_elogbeta,
-                  nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
-    const int grid = grid_for_warps(D, 8, 8);
-    int rc = launch_doc_pass<false>(P, grid, s);
+                  nullptr, nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
+    int rc = launch_doc_pass<false>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("elbo_tokens");
-    return launch_reduce_records((const double*)workspace, grid, partial_out, s);
+    return launch_reduce_records((const double*)workspace, grid_for_warps(D, kDocThreads / 32, 16), partial_out, s);
 }
 
 }  // extern "C"

@@ -7,65 +7,62 @@
 // phi (D x N x K) is never materialised; not even the per-nonzero normaliser is stored — it is recomputed from the
 // gathered eT row (K FMAs), which is cheaper than 12 more bytes per nonzero of HBM traffic.
 //
+// Mapping (traverse.cuh): the word's exp(E[log beta_w]) K-vector is replicated over the warp's R = 32/G lane
+// groups; each group gathers the exp(E[log theta_d]) K-vector of a different posting, R postings per instruction;
+// group partials are summed through shared memory when the word's segment ends.
+//
 // Work decomposition: the nnz CSC positions are cut into fixed chunks (nnz-balanced, immune to Zipfian posting
 // lists); one warp per chunk walks the words intersecting it.  A word that lies wholly inside a chunk is written
 // with a plain store; a word cut by a chunk boundary contributes one partial K-vector per chunk, written to a
 // carry buffer and summed in chunk order by a second kernel => bit-reproducible, no atomics.
-// Bound: HBM gather of 8K bytes per nonzero (eT rows, D x K table, far larger than L2 at the target sizes).
-#include "ttlda_common.cuh"
+//
+// The CSC mirror may be DOCUMENT-BLOCKED (ttlda_csr_to_csc with nblocks > 1): "virtual word" b*V + w holds the
+// postings of word w inside document block b, so that consecutive chunks gather eT rows from one block-sized
+// window of the D x K table that stays resident in the 126 MB L2; the per-block partial statistics are summed in
+// block order by sstats_fold_kernel.  Bound: gather of 8K bytes per nonzero (HBM unblocked, L2 blocked).
+#include "traverse.cuh"
 
 namespace ttlda {
 
-constexpr int kChunk = 512;  // CSC positions per warp work item
+constexpr int kChunk = 512;       // CSC positions per warp work item
+constexpr int kWordThreads = 128;  // 4 warps per CTA
 
 struct SStatsParams {
-    const int64_t* colptr;
+    const int64_t* colptr;  // [VV+1], VV = nblocks * V virtual words
     const int32_t* docidx;
     const int32_t* ccounts;
     int64_t V;
+    int64_t VV;
     int K;
     int64_t ld;
     int64_t nnz;
     int64_t nchunks;
     const double* eT;
     const double* eB;
-    double* S;
+    double* S;           // [VV][ld] per-(block, word) statistics (== the final [V][ld] table when nblocks == 1)
     double* carry;       // [nchunks][2][ld]  head / tail partials of words cut by a chunk boundary
-    int32_t* carry_word; // [nchunks][2]      word id of each carry slot, -1 = unused
+    int32_t* carry_word; // [nchunks][2]      virtual word id of each carry slot, -1 = unused
 };
 
-template <int KP>
-__device__ __forceinline__ void load_row2(double2 (&v)[KP], const double* __restrict__ row, int lane, int ld)
+template <int G, int E, bool PREFETCH>
+__global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsParams P)
 {
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        const int k = 2 * lane + 64 * j;
-        v[j] = (k < ld) ? ldg2(row + k) : make_double2(0., 0.);
-    }
-}
+    constexpr int R = 32 / G;
+    constexpr int LDP = 2 * G * E;
+    constexpr int MMAX = (LDP + 31) / 32;
+    extern __shared__ double smem[];
+    double* wbuf = smem + (threadIdx.x >> 5) * (R * LDP);
 
-template <int KP>
-__device__ __forceinline__ void store_row2(const double2 (&v)[KP], double* __restrict__ row, int lane, int ld)
-{
-#pragma unroll
-    for (int j = 0; j < KP; ++j) {
-        const int k = 2 * lane + 64 * j;
-        if (k < ld) *reinterpret_cast<double2*>(row + k) = v[j];
-    }
-}
-
-template <int KP, bool PREFETCH>
-__global__ void __launch_bounds__(256) sstats_csc_kernel(const SStatsParams P)
-{
     const int lane = threadIdx.x & 31;
+    const int g = lane % G, r = lane / G;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld;
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
         const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
-        // first word with colptr[w+1] > cb  (upper_bound over colptr[1..V])
-        int64_t lo = 0, hi = P.V;  // search w in [0, V)
+        // first virtual word with colptr[w+1] > cb
+        int64_t lo = 0, hi = P.VV;
         while (lo < hi) {
             const int64_t mid = (lo + hi) >> 1;
             if (P.colptr[mid + 1] > cb) hi = mid; else lo = mid + 1;
@@ -78,16 +75,15 @@ __global__ void __launch_bounds__(256) sstats_csc_kernel(const SStatsParams P)
         int64_t pos = cb;
         while (pos < ce) {
             int64_t wb = P.colptr[w], we = P.colptr[w + 1];
-            while (we <= pos) {  // skip words with empty posting lists
+            while (we <= pos) {  // skip (virtual) words with empty posting lists
                 ++w;
                 wb = we;
                 we = P.colptr[w + 1];
             }
-            const int64_t se = (we < ce) ? we : ce;  // segment [pos, se) of word w
-            double2 b[KP], acc[KP];
-            load_row2<KP>(b, P.eB + w * P.ld, lane, ld);
-#pragma unroll
-            for (int j = 0; j < KP; ++j) acc[j] = make_double2(0., 0.);
+            const int64_t se = (we < ce) ? we : ce;  // segment [pos, se) of virtual word w
+            KSlice<G, E> b, acc;
+            b.load(P.eB + (w % P.V) * P.ld, g, ld);
+            acc.zero();
 
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
@@ -96,73 +92,79 @@ __global__ void __launch_bounds__(256) sstats_csc_kernel(const SStatsParams P)
                     my_d = ld_stream_s32(P.docidx + n0 + lane);
                     my_c = ld_stream_s32(P.ccounts + n0 + lane);
                 }
-                double2 cur[KP], nxt[KP];
-                {
-                    const int d0 = __shfl_sync(0xffffffffu, my_d, 0);
-                    load_row2<KP>(cur, P.eT + (int64_t)d0 * P.ld, lane, ld);
-                }
-                for (int i = 0; i < cnt; ++i) {
-                    if (PREFETCH && i + 1 < cnt) {
-                        const int dn = __shfl_sync(0xffffffffu, my_d, i + 1);
-                        load_row2<KP>(nxt, P.eT + (int64_t)dn * P.ld, lane, ld);
-                    }
-                    const int cc = __shfl_sync(0xffffffffu, my_c, i);
-                    double p = 0.;
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) {
-                        p = fma(cur[j].x, b[j].x, p);
-                        p = fma(cur[j].y, b[j].y, p);
-                    }
-                    p = warp_sum(p);
-                    const double r = (double)cc / (p + 1e-100);  // lda_model.py:242,262
-#pragma unroll
-                    for (int j = 0; j < KP; ++j) {
-                        acc[j].x = fma(r, cur[j].x, acc[j].x);
-                        acc[j].y = fma(r, cur[j].y, acc[j].y);
-                    }
+                const int nsub = (cnt + R - 1) / R;
+                KSlice<G, E> cur, nxt;
+                cur.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, r) * P.ld, g, ld);
+                for (int s = 0; s < nsub; ++s) {
+                    const int i = s * R + r;
+                    if (PREFETCH && s + 1 < nsub)
+                        nxt.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, i + R) * P.ld, g, ld);
+                    const int cc = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt
+                    const double p = group_sum<G>(b.dot(cur));
+                    const double rr = (double)cc / (p + 1e-100);  // lda_model.py:242,262
+                    acc.axpy(rr, cur);
                     if (PREFETCH) {
-#pragma unroll
-                        for (int j = 0; j < KP; ++j) cur[j] = nxt[j];
-                    } else if (i + 1 < cnt) {
-                        const int dn = __shfl_sync(0xffffffffu, my_d, i + 1);
-                        load_row2<KP>(cur, P.eT + (int64_t)dn * P.ld, lane, ld);
+                        cur = nxt;
+                    } else if (s + 1 < nsub) {
+                        cur.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, i + R) * P.ld, g, ld);
                     }
                 }
             }
+            // group partials -> one K-vector, written with coalesced stores
+            acc.to_smem(wbuf + r * LDP, g);
+            __syncwarp();
             const bool whole = (pos == wb) && (se == we);
-            if (whole) {
-                store_row2<KP>(acc, P.S + w * P.ld, lane, ld);
-            } else {
-                // head slot: the word was started by an earlier chunk; tail slot: it continues in a later one.
-                // A word spanning the entire chunk (neither starts nor ends here) uses the head slot.
-                const int slot = (pos != wb) ? 0 : 1;
-                store_row2<KP>(acc, P.carry + (c * 2 + slot) * P.ld, lane, ld);
-                if (lane == 0) P.carry_word[c * 2 + slot] = (int32_t)w;
+            // head slot: the word was started by an earlier chunk; tail slot: it continues in a later one.
+            // A word spanning the entire chunk (neither starts nor ends here) uses the head slot.
+            const int slot = (pos != wb) ? 0 : 1;
+            double* dst = whole ? P.S + w * P.ld : P.carry + (c * 2 + slot) * P.ld;
+#pragma unroll
+            for (int m = 0; m < MMAX; ++m) {
+                const int k = lane + 32 * m;
+                if (k < ld) {
+                    double a = 0.;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
+                    dst[k] = a;
+                }
             }
+            __syncwarp();
+            if (!whole && lane == 0) P.carry_word[c * 2 + slot] = (int32_t)w;
             pos = se;
             if (se == we) ++w;
         }
     }
 }
 
-// Sum the carries of each cut word in chunk order.  One warp per chunk whose TAIL slot is in use (= the chunk
-// where a cut word starts); it walks the following chunks' HEAD slots while they name the same word.
+// Sum the carries of each cut word in chunk order.  One warp per chunk whose TAIL slot is in use (= the chunk in
+// which a cut word starts); it walks the following chunks' HEAD slots while they name the same word.
 __global__ void __launch_bounds__(256) sstats_carry_kernel(const SStatsParams P)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
-        // a cut word starts in chunk c either in its tail slot, or — if chunk c begins exactly at the word's first
-        // posting and the word outlives the chunk — also in the tail slot (pos == wb there), so tail is the start.
         const int32_t w = P.carry_word[c * 2 + 1];
         if (w < 0) continue;
+        int64_t last = c;
+        while (last + 1 < P.nchunks && P.carry_word[(last + 1) * 2 + 0] == w) ++last;
         for (int k = lane; k < (int)P.ld; k += 32) {
             double s = P.carry[(c * 2 + 1) * P.ld + k];
-            for (int64_t c2 = c + 1; c2 < P.nchunks && P.carry_word[c2 * 2 + 0] == w; ++c2)
-                s += P.carry[(c2 * 2 + 0) * P.ld + k];
+            for (int64_t c2 = c + 1; c2 <= last; ++c2) s += P.carry[(c2 * 2 + 0) * P.ld + k];
             P.S[(int64_t)w * P.ld + k] = s;
         }
+    }
+}
+
+// S[w][k] = sum_b Sb[b*V + w][k] in block order (document-blocked mirror only)
+__global__ void __launch_bounds__(256) sstats_fold_kernel(const double* __restrict__ Sb, int64_t V, int64_t ld,
+                                                          int nblocks, double* __restrict__ S)
+{
+    const int64_t total = V * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.;
+        for (int b = 0; b < nblocks; ++b) s += Sb[(int64_t)b * total + i];
+        S[i] = s;
     }
 }
 
@@ -170,59 +172,90 @@ static int64_t nchunks_for(int64_t nnz) { return (nnz + kChunk - 1) / kChunk; }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+template <int G, int E>
+static void launch_shape(const SStatsParams& P, int grid, cudaStream_t s)
+{
+    constexpr int R = 32 / G;
+    constexpr size_t smem = (size_t)(kWordThreads / 32) * R * 2 * G * E * sizeof(double);
+    constexpr bool PF = (E <= 8);
+    sstats_csc_kernel<G, E, PF><<<grid, kWordThreads, smem, s>>>(P);
+}
+
 }  // namespace ttlda
 
 using namespace ttlda;
 
 extern "C" {
 
-int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld)
+int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks)
 {
-    (void)V;
     const int64_t nc = nchunks_for(nnz);
-    return (int64_t)(align256((size_t)nc * 2 * ld * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t)) + 256);
+    size_t b = align256((size_t)nc * 2 * ld * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t)) + 256;
+    if (nblocks > 1) b += align256((size_t)nblocks * V * ld * sizeof(double));
+    return (int64_t)b;
 }
 
 int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t V, int64_t K,
-                         int64_t ld, int64_t nnz, const double* exp_elogtheta, const double* exp_elogbeta,
-                         double* sstats, void* workspace, int64_t workspace_bytes, void* stream)
+                         int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
+                         const double* exp_elogbeta, double* sstats, void* workspace, int64_t workspace_bytes,
+                         void* stream)
 {
     TTLDA_REQUIRE(colptr && exp_elogtheta && exp_elogbeta && sstats && workspace, "NULL pointer");
     TTLDA_REQUIRE(V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
-    TTLDA_REQUIRE(ld >= K && ld % 4 == 0, "ld must be a multiple of 4 and >= K");
-    if (workspace_bytes < ttlda_sstats_workspace_bytes(nnz, V, ld)) {
+    TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
+    TTLDA_REQUIRE(nblocks >= 1 && nblocks * V < ((int64_t)1 << 31), "bad nblocks");
+    if (workspace_bytes < ttlda_sstats_workspace_bytes(nnz, V, ld, nblocks)) {
         set_error("sstats_csc: workspace %lld < %lld", (long long)workspace_bytes,
-                  (long long)ttlda_sstats_workspace_bytes(nnz, V, ld));
+                  (long long)ttlda_sstats_workspace_bytes(nnz, V, ld, nblocks));
         return TTLDA_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(sstats, 0, (size_t)V * ld * sizeof(double), s);  // words with no postings
-    if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
-    if (nnz == 0 || V == 0) return TTLDA_OK;
     const int64_t nc = nchunks_for(nnz);
-    SStatsParams P{colptr, docidx, ccounts, V, (int)K, ld, nnz, nc, exp_elogtheta, exp_elogbeta, sstats,
-                   (double*)workspace,
-                   (int32_t*)((char*)workspace + align256((size_t)nc * 2 * ld * sizeof(double)))};
-    const int grid = grid_for_warps(nc, 8, 8);
-    const int need = (int)((ld + 63) / 64);
-    bool launched = false;
-#define TTLDA_CASE(KP, PF)                                   \
-    if (!launched && need <= KP) {                           \
-        sstats_csc_kernel<KP, PF><<<grid, 256, 0, s>>>(P);   \
-        launched = true;                                     \
+    char* ws = (char*)workspace;
+    double* carry = (double*)ws;
+    int32_t* carry_word = (int32_t*)(ws + align256((size_t)nc * 2 * ld * sizeof(double)));
+    double* Sb = (nblocks > 1)
+                     ? (double*)((char*)carry_word + align256((size_t)nc * 2 * sizeof(int32_t)))
+                     : sstats;
+    const int64_t VV = nblocks * V;
+    cudaError_t e = cudaMemsetAsync(Sb, 0, (size_t)VV * ld * sizeof(double), s);  // words with no postings
+    if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
+    if (nnz == 0 || V == 0) {
+        if (nblocks > 1) {
+            e = cudaMemsetAsync(sstats, 0, (size_t)V * ld * sizeof(double), s);
+            if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
+        }
+        return TTLDA_OK;
     }
-    TTLDA_CASE(1, true)
-    TTLDA_CASE(2, true)
-    TTLDA_CASE(3, true)
-    TTLDA_CASE(4, true)
-    TTLDA_CASE(6, false)
-    TTLDA_CASE(8, false)
-    TTLDA_CASE(12, false)
-    TTLDA_CASE(16, false)
+    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, nnz, nc, exp_elogtheta, exp_elogbeta, Sb, carry,
+                   carry_word};
+    const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
+    GroupShape gs = group_shape_for(ld);
+    if (const char* ov = getenv("TTLDA_GROUP")) {
+        const int G = atoi(ov);
+        if (G == 2 || G == 4 || G == 8 || G == 16 || G == 32) gs = {G, (int)((ld + 2 * G - 1) / (2 * G))};
+    }
+    bool launched = false;
+#define TTLDA_CASE(GG, EE)                        \
+    if (!launched && gs.G == GG && gs.E == EE) {  \
+        launch_shape<GG, EE>(P, grid, s);         \
+        launched = true;                          \
+    }
+    TTLDA_FOR_EACH_SHAPE(TTLDA_CASE)
 #undef TTLDA_CASE
+    if (!launched) {
+        set_error("no kernel instantiated for ld=%lld (G=%d, E=%d)", (long long)ld, gs.G, gs.E);
+        return TTLDA_EINVAL;
+    }
     TTLDA_LAUNCH_CHECK("sstats_csc");
-    sstats_carry_kernel<<<grid, 256, 0, s>>>(P);
+    sstats_carry_kernel<<<grid_for_warps(nc, 8, 8), 256, 0, s>>>(P);
     TTLDA_LAUNCH_CHECK("sstats_carry");
+    if (nblocks > 1) {
+        const int64_t total = V * ld;
+        int fg = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
+        sstats_fold_kernel<<<fg, 256, 0, s>>>(Sb, V, ld, (int)nblocks, sstats);
+        TTLDA_LAUNCH_CHECK("sstats_fold");
+    }
     return TTLDA_OK;
 }
 

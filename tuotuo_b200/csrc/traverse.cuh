@@ -1,0 +1,96 @@
+// traverse.cuh — the group-mapped K-vector traversal shared by the document-major (E-step / ELBO) and word-major
+// (sufficient statistics) passes.
+//
+// A K-vector (one row of a [.][ld] fp64 table) is owned by a GROUP of G lanes, G in {2,4,8,16,32}; a warp holds
+// R = 32/G groups and therefore processes R nonzeros at once.  Lane g of a group owns the E double2 slices
+//     k = 2*(g + G*j), j = 0..E-1                      (ld <= 2*G*E)
+// so each load instruction reads G*16 contiguous bytes per group (coalesced, 16-byte aligned since ld % 4 == 0).
+//
+// Why groups instead of one warp per K-vector: per nonzero the fixed costs — the shuffle reduction of the dot
+// product (log2 G steps instead of 5), the fp64 division (~25 instructions) and the index broadcasts — are paid
+// once per R nonzeros, and each lane has E (not K/64) independent 16-byte loads in flight, E more when the next
+// sub-batch is prefetched.  For K = 100: G = 8, E = 7, R = 4 => ~20 warp instructions per nonzero instead of ~130
+// (ncu, profiles/r01a), which moves the passes from issue-bound to memory-bound.
+#pragma once
+
+#include "ttlda_common.cuh"
+
+namespace ttlda {
+
+template <int G, int E>
+struct KSlice {
+    double2 v[E];
+
+    __device__ __forceinline__ void load(const double* __restrict__ row, int g, int ld)
+    {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const int k = 2 * (g + G * j);
+            v[j] = (k < ld) ? ldg2(row + k) : make_double2(0., 0.);
+        }
+    }
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < E; ++j) v[j] = make_double2(0., 0.);
+    }
+    // partial dot product over this lane's slices
+    __device__ __forceinline__ double dot(const KSlice& o) const
+    {
+        double p0 = 0., p1 = 0.;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            p0 = fma(v[j].x, o.v[j].x, p0);
+            p1 = fma(v[j].y, o.v[j].y, p1);
+        }
+        return p0 + p1;
+    }
+    __device__ __forceinline__ void axpy(double a, const KSlice& x)
+    {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            v[j].x = fma(a, x.v[j].x, v[j].x);
+            v[j].y = fma(a, x.v[j].y, v[j].y);
+        }
+    }
+    // write this lane's slices into a [.. 2*G*E] shared-memory row (group-partial K-vector)
+    __device__ __forceinline__ void to_smem(double* row, int g) const
+    {
+#pragma unroll
+        for (int j = 0; j < E; ++j) *reinterpret_cast<double2*>(row + 2 * (g + G * j)) = v[j];
+    }
+};
+
+// sum over the G lanes of a group (result in every lane of the group)
+template <int G>
+__device__ __forceinline__ double group_sum(double p)
+{
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    return p;
+}
+
+// (G, E) for a leading dimension: the smallest group that keeps E <= 8 slices per lane (E <= 16 for full warps)
+struct GroupShape {
+    int G, E;
+};
+
+inline GroupShape group_shape_for(int64_t ld)
+{
+    for (int G = 2; G <= 32; G *= 2) {
+        const int E = (int)((ld + 2 * G - 1) / (2 * G));
+        if (E <= 8 || G == 32) return {G, E};
+    }
+    return {32, 16};
+}
+
+// Expands X(G, E) for every instantiated shape.
+#define TTLDA_FOR_EACH_SHAPE(X)                                                                      \
+    X(2, 1) X(2, 2) X(2, 3) X(2, 4) X(2, 5) X(2, 6) X(2, 7) X(2, 8)                                   \
+    X(4, 5) X(4, 6) X(4, 7) X(4, 8)                                                                   \
+    X(8, 5) X(8, 6) X(8, 7) X(8, 8)                                                                   \
+    X(16, 4) X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                                      \
+    X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8) X(32, 9) X(32, 10) X(32, 11) X(32, 12) X(32, 13) X(32, 14) \
+    X(32, 15) X(32, 16)
+
+}  // namespace ttlda

@@ -9,11 +9,14 @@ access.  There is NO CPU path: without a CUDA device / the built library every c
 
 Per EM iteration (tuotuo/lda_model.py:285-316 + :403-409):
     ttlda_estep_f64        gamma, exp(E[log theta]) refresh, theta-prior term        (e_step :197-270, :142-148)
+                           + the ELBO token term of the INCOMING state (:125-139): it is the same dot product the
+                           E-step normaliser needs, so the perplexity of iteration t is a by-product of E-step t+1
+    [48-byte D2H]          perplexity of the incoming state -> the reference's convergence test (:386-390); the
+                           E-step wrote into ping-pong buffers, so on "converged" it is simply discarded
     ttlda_sstats_csc_f64   K x V sufficient statistics, word-major, no atomics       (:262)
     [NCCL all_reduce]      documents are sharded across ranks; sum the statistics    
     ttlda_mstep_f64        lambda, exp(E[log beta]) refresh, beta-prior term         (:264, m_step :273-283, :157-163)
-    ttlda_elbo_tokens_f64  token term of the ELBO at the new state                   (:125-139)
-and one 3-double device->host read for the perplexity / convergence test.
+After the last iteration one ttlda_elbo_tokens_f64 pass yields the final perplexity.
 """
 from __future__ import annotations
 
@@ -123,19 +126,22 @@ class LDASmoothed:
         st = _State()
         st.dev, st.corpus, st.K, st.V, st.D, st.ld = dev, corpus, K, V, D, ld
         f64 = torch.float64
-        st.gamma = torch.zeros((D, ld), dtype=f64, device=dev)
+        st.gamma = [torch.zeros((D, ld), dtype=f64, device=dev), torch.zeros((D, ld), dtype=f64, device=dev)]
         st.eT = [torch.zeros((D, ld), dtype=f64, device=dev), torch.zeros((D, ld), dtype=f64, device=dev)]
         st.cur = 0
         st.lam = torch.zeros((V, ld), dtype=f64, device=dev)
         st.eB = torch.zeros((V, ld), dtype=f64, device=dev)
         st.sstats = torch.zeros((V, ld), dtype=f64, device=dev)
         st.colsum = torch.zeros(ld, dtype=f64, device=dev)
-        st.part = torch.zeros((4, nv.NPART), dtype=f64, device=dev)
+        st.part = torch.zeros((5, nv.NPART), dtype=f64, device=dev)
         st.iters = torch.zeros(2, dtype=torch.int64, device=dev)
         st.ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
         st.ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
-        st.ws_s = (torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld), dtype=torch.uint8, device=dev)
-                   if self._sstats_mode == "csc" else None)
+        st.ws_s = None
+        if self._sstats_mode == "csc":
+            corpus.ensure_csc(ld)  # (document-blocked) CSC mirror sized for this K
+            st.ws_s = torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld, corpus.nblocks), dtype=torch.uint8,
+                                  device=dev)
         st.terms = dict(tok=0.0, theta=0.0, beta=0.0, count=0.0)
         self._st = st
         self._np_cache = {}
@@ -172,7 +178,7 @@ class LDASmoothed:
             raise AttributeError("'LDASmoothed' object has no attribute '_gamma_'")
         if "gamma" not in self._np_cache:
             st = self._st
-            local = st.gamma[:, :st.K].contiguous()
+            local = st.gamma[st.cur][:, :st.K].contiguous()
             dist = self._dist()
             if dist is not None:  # gather the document shards in rank order
                 sizes = [torch.zeros(1, dtype=torch.int64, device=st.dev) for _ in range(dist.get_world_size())]
@@ -193,8 +199,8 @@ class LDASmoothed:
             raise AttributeError("fit() first")
         v = torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64)).to(st.dev)
         assert v.shape == (st.D, st.K)
-        st.gamma.zero_()
-        st.gamma[:, :st.K] = v
+        st.gamma[st.cur].zero_()
+        st.gamma[st.cur][:, :st.K] = v
         self._np_cache.pop("gamma", None)
 
     def _invalidate(self, *names):
@@ -206,11 +212,11 @@ class LDASmoothed:
     # ------------------------------------------------------------------------------------------------------------------
     def _refresh_theta(self):
         st = self._st
-        nv.theta_refresh(st.gamma, st.K, st.alpha_vec, self._alpha_sum(), st.eT[st.cur], st.part[1], st.ws)
+        nv.theta_refresh(st.gamma[st.cur], st.K, st.alpha_vec, self._alpha_sum(), st.eT[st.cur], st.part[1], st.ws)
 
     def _refresh_theta_term_only(self):
         st = self._st
-        nv.theta_refresh(st.gamma, st.K, st.alpha_vec, self._alpha_sum(), None, st.part[1], st.ws)
+        nv.theta_refresh(st.gamma[st.cur], st.K, st.alpha_vec, self._alpha_sum(), None, st.part[1], st.ws)
 
     def _refresh_beta(self):
         st = self._st
@@ -220,30 +226,38 @@ class LDASmoothed:
         st, c = self._st, self._st.corpus
         nv.elbo_tokens(c.rowptr, c.colidx, c.counts, st.K, st.eT[st.cur], st.eB, st.part[3], st.ws)
 
-    def _em_iteration(self, e_num_step: int, e_threshold: float = 1e-05):
-        """One em_step (lda_model.py:285-316) followed by the token term of the next perplexity."""
+    def _estep_speculative(self, e_num_step: int, e_threshold: float = 1e-05):
+        """E-step (lda_model.py:197-270) from the current state into the ping-pong buffers.  By-product: the ELBO
+        token term of the CURRENT state (part[0][0]), which completes its perplexity."""
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
         atomic = self._sstats_mode == "atomic"
         if atomic:
             st.sstats.zero_()
         nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma, st.eT[nxt], st.sstats if atomic else None, e_num_step, e_threshold, st.iters, st.part[0],
-                 st.ws)
-        if not atomic:
-            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, st.eT[cur], st.eB, st.sstats, st.ws_s)
+                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], st.sstats if atomic else None, e_num_step, e_threshold,
+                 st.iters, st.part[0], st.ws)
+
+    def _commit_iteration(self):
+        """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
+        adopt the E-step's gamma / exp(E[log theta])."""
+        st, c = self._st, self._st.corpus
+        if self._sstats_mode != "atomic":
+            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[st.cur], st.eB, st.sstats,
+                          st.ws_s)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink (SURVEY §8e)
         nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
-        st.cur = nxt
-        self._tokens()
+        st.cur ^= 1
         self._invalidate()
 
-    def _collect(self, theta_row: int):
-        """One device->host read of the ELBO terms (summed over ranks when sharded)."""
+    def _collect(self, tok_row: int):
+        """One device->host read of the terms of the CURRENT state's ELBO (summed over ranks when sharded).
+        tok_row = 0: token term / token count from the speculative E-step record; 3: from ttlda_elbo_tokens_f64.
+        The theta-prior and beta-prior terms of the current state are kept in part[1][0] and part[2][0]."""
         st = self._st
-        buf = torch.stack([st.part[3, 0], st.part[theta_row, 1 if theta_row == 0 else 0], st.part[3, 2],
+        buf = torch.stack([st.part[tok_row, 0], st.part[1, 0], st.part[tok_row, 2],
                            st.iters[0].to(torch.float64), st.iters[1].to(torch.float64), st.part[2, 0]])
         dist = self._dist()
         if dist is not None:
@@ -303,35 +317,41 @@ class LDASmoothed:
             print(f"Var Inf - Word Dirichlet prior, Lambda")
             print((K, V))
             print()
-        st.gamma.zero_()  # lda_model.py:364: alpha + ones * V / K
-        st.gamma[:, :K] = st.alpha_vec + float(V) / float(K)
+        st.gamma[st.cur].zero_()  # lda_model.py:364: alpha + ones * V / K
+        st.gamma[st.cur][:, :K] = st.alpha_vec + float(V) / float(K)
         if verbose:
             print(f"Var Inf - Topic Dirichlet prior, Gamma")
             print((self.M, K))
             print()
 
         perplexities = []
+        perplexity = np.inf
         self._refresh_theta()
         self._refresh_beta()
-        self._tokens()
-        self._collect(theta_row=1)
-        perplexity = self._perplexity_from_terms(sampling)  # lda_model.py:373-378
-        perplexities.append(np.float64(perplexity))
-        if verbose:
-            print(f"Init perplexity = {perplexity}")
-
-        delta_perplexity = np.inf
-        for _ in range(em_num_step):  # lda_model.py:384
-            if delta_perplexity < threshold:  # :386-390 early return, skips the hyper-parameter update
+        for it in range(em_num_step):  # lda_model.py:384
+            # E-step `it` also completes the perplexity of state `it` (initial perplexity for it == 0, :373-378;
+            # perplexity after em_step it-1 otherwise, :403-409)
+            self._estep_speculative(e_num_step)
+            _, capped = self._collect(tok_row=0)
+            perplexity_orig, perplexity = perplexity, self._perplexity_from_terms(sampling)
+            perplexities.append(np.float64(perplexity))
+            if it == 0 and verbose:
+                print(f"Init perplexity = {perplexity}")
+            if it > 0 and perplexity_orig - perplexity < threshold:
+                # :386-390 early return (also skips the hyper-parameter update); the speculative E-step is dropped
                 return perplexities if return_perplexities else None
-            perplexity_orig = perplexity
-            self._em_iteration(e_num_step)
-            _, capped = self._collect(theta_row=0)
             if capped:
                 warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
-            perplexity = self._perplexity_from_terms(sampling)  # :403-409
-            perplexities.append(np.float64(perplexity))
-            delta_perplexity = perplexity_orig - perplexity
+            # the theta-prior term of the state being adopted was produced by the E-step (record entry 1)
+            st.part[1, 0].copy_(st.part[0, 1])
+            self._commit_iteration()
+        # perplexity of the final state (or the initial one when em_num_step == 0)
+        self._tokens()
+        self._collect(tok_row=3)
+        perplexity = self._perplexity_from_terms(sampling)
+        perplexities.append(np.float64(perplexity))
+        if em_num_step == 0 and verbose:
+            print(f"Init perplexity = {perplexity}")
 
         if update_hyper_parms:  # lda_model.py:414-424
             self.update_alpha()
@@ -340,7 +360,7 @@ class LDASmoothed:
             # (exp(E[log beta]) is rewritten with identical values: it does not depend on eta)
             self._refresh_theta_term_only()
             self._refresh_beta()
-            self._collect(theta_row=1)
+            self._collect(tok_row=3)
             perplexity = self._perplexity_from_terms(sampling)
             perplexities.append(np.float64(perplexity))
 
@@ -355,8 +375,8 @@ class LDASmoothed:
     def _gamma_psi_stat(self) -> float:
         """sum_dk psi(gamma_dk) - K * sum_d psi(sum_k gamma_dk)   (loop-invariant part of lda_model.py:459-462)."""
         st = self._st
-        nv.hyper_stats(st.gamma, st.K, st.part[1], st.ws)
-        v = st.part[1, :2].clone()
+        nv.hyper_stats(st.gamma[st.cur], st.K, st.part[4], st.ws)
+        v = st.part[4, :2].clone()
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(v)
@@ -366,10 +386,10 @@ class LDASmoothed:
     def _lambda_psi_stat(self) -> float:
         """sum_kv psi(lambda_kv) - V * sum_k psi(sum_v lambda_kv)   (lda_model.py:522-528)."""
         st = self._st
-        nv.hyper_stats(st.lam, st.K, st.part[1], st.ws)
+        nv.hyper_stats(st.lam, st.K, st.part[4], st.ws)
         pc = torch.empty(st.K, dtype=torch.float64, device=st.dev)
         nv.psi_exact(st.colsum[:st.K].contiguous(), pc)
-        return float(st.part[1, 0].item() - st.V * pc.sum().item())
+        return float(st.part[4, 0].item() - st.V * pc.sum().item())
 
     def update_alpha(self, step: int = 500, threshold: float = 1e-07, verbose: bool = False) -> None:
         if isinstance(self._alpha_, np.ndarray):
@@ -420,8 +440,8 @@ class LDASmoothed:
     # ------------------------------------------------------------------------------------------------------------------
     def _elog_np(self):
         st = self._st
-        et = torch.empty_like(st.gamma)
-        nv.dirichlet_expectation(st.gamma, st.K, out_elog=et)
+        et = torch.empty_like(st.gamma[st.cur])
+        nv.dirichlet_expectation(st.gamma[st.cur], st.K, out_elog=et)
         eb = torch.empty_like(st.lam)
         self_colwise = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
         nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB.clone(), eb, st.colsum, st.part[2], st.ws_m)
@@ -458,7 +478,7 @@ class LDASmoothed:
         st = self._st
         nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB.clone(), None, st.colsum, st.part[2], st.ws_m)
         self._tokens()
-        self._collect(theta_row=1)
+        self._collect(tok_row=3)
         self._perplexity_from_terms(sampling)
         if expec_log_theta is None or expec_log_beta is None:
             et, eb = self._elog_np()
@@ -479,10 +499,10 @@ class LDASmoothed:
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
         nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma, st.eT[nxt], None, step, threshold, st.iters, st.part[0], st.ws)
-        ws_s = st.ws_s if st.ws_s is not None else torch.empty(nv.sstats_workspace_bytes(c.nnz, st.V, st.ld),
-                                                               dtype=torch.uint8, device=st.dev)
-        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, st.eT[cur], st.eB, st.sstats, ws_s)
+                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], None, step, threshold, st.iters, st.part[0], st.ws)
+        c.ensure_csc(st.ld)
+        ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, st.V, st.ld, c.nblocks), dtype=torch.uint8, device=st.dev)
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[cur], st.eB, st.sstats, ws_s)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)
@@ -493,8 +513,8 @@ class LDASmoothed:
         capped = int(st.iters[1].item())
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {step + 1} for {capped} documents")
-        et = torch.empty_like(st.gamma)
-        nv.dirichlet_expectation(st.gamma, st.K, out_elog=et)
+        et = torch.empty_like(st.gamma[st.cur])
+        nv.dirichlet_expectation(st.gamma[st.cur], st.K, out_elog=et)
         return self._gamma_, (upd.cpu().numpy(), et[:, :st.K].cpu().numpy())
 
     def m_step(self, lambda_update, verbose: bool = False, batch: bool = True):
