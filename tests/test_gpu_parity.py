@@ -392,14 +392,14 @@ def test_blocked_and_unblocked_statistics_agree(monkeypatch):
     assert relerr(res["1"][1], res["7"][1]) < 1e-12 and relerr(res["1"][2], res["7"][2]) < 1e-12
 
 
-@pytest.mark.parametrize("G", ["2", "4", "8", "16", "32"])
-def test_every_group_width_is_exact(monkeypatch, G):
+@pytest.mark.parametrize("G,K", [("2", 30), ("4", 60), ("8", 100), ("16", 100), ("16", 250), ("32", 300)])
+def test_every_group_width_is_exact(monkeypatch, G, K):
     """TTLDA_GROUP forces the lanes-per-K-vector mapping; every width must give the same answer as the oracle."""
     from tuotuo.document import Document
     from tuotuo.lda_model import LDASmoothed
     from tuotuo_b200.synth import numpy_corpus
 
-    K, V = 30, 500  # ld = 32: representable with every G (E = 8, 4, 2, 1, 1)
+    V = 500
     rp, ci, ct = numpy_corpus(33, 150, V, 12, 45, ragged=True)
     o = OracleLDA(K, engine="c")
     po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=2)

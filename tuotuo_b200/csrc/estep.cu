@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld, K = P.K;
+    const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
 
     double lga = 0., lg_asum = 0.;
     if (ESTEP) {
@@ -71,7 +72,7 @@ __global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams
     for (int64_t d = warp0; d < P.D; d += nwarps) {
         const int64_t b = P.rowptr[d], e = P.rowptr[d + 1];
         KSlice<G, E> t, acc;
-        t.load(P.eT_in + d * P.ld, g, ld);
+        t.load(P.eT_in + d * P.ld, g, last_ok);
         acc.zero();
 
         for (int64_t n0 = b; n0 < e; n0 += 32) {
@@ -82,38 +83,30 @@ __global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams
                 my_c = ld_stream_s32(P.counts + n0 + lane);
             }
             double my_p = 1.;
-            const int nsub = (cnt + R - 1) / R;
-            KSlice<G, E> cur, nxt;
-            cur.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, r) * P.ld, g, ld);
-            for (int s = 0; s < nsub; ++s) {
-                const int i = s * R + r;  // nonzero handled by this group in this sub-batch
-                if (PREFETCH && s + 1 < nsub)
-                    nxt.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, i + R) * P.ld, g, ld);
+            walk_rows<G, E, PREFETCH>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
+                const int i = s * R + r;                          // nonzero handled by this group in this sub-batch
                 const int c = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt: the group idles harmlessly
-                const int wi = __shfl_sync(0xffffffffu, my_w, i);
-                const double p = group_sum<G>(t.dot(cur));
+                const double p = group_sum<G>(t.dot(row));
                 if (ESTEP) {
                     const double rr = (double)c / (p + 1e-100);
-                    acc.axpy(rr, cur);
-                    if (P.sstats_atomic && c) {
-                        double* srow = P.sstats_atomic + (int64_t)wi * P.ld;
+                    acc.axpy(rr, row);
+                    if (P.sstats_atomic) {  // warp-uniform branch
+                        const int wi = __shfl_sync(0xffffffffu, my_w, i);
+                        if (c) {
+                            double* srow = P.sstats_atomic + (int64_t)wi * P.ld;
 #pragma unroll
-                        for (int j = 0; j < E; ++j) {
-                            const int k = 2 * (g + G * j);
-                            if (k < K) atomicAdd(srow + k, t.v[j].x * rr);
-                            if (k + 1 < K) atomicAdd(srow + k + 1, t.v[j].y * rr);
+                            for (int j = 0; j < E; ++j) {
+                                const int k = 2 * (g + G * j);
+                                if (k < K) atomicAdd(srow + k, t.v[j].x * rr);
+                                if (k + 1 < K) atomicAdd(srow + k + 1, t.v[j].y * rr);
+                            }
                         }
                     }
                 }
                 // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == s) my_p = pv;
-                if (PREFETCH) {
-                    cur = nxt;
-                } else if (s + 1 < nsub) {
-                    cur.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, my_w, i + R) * P.ld, g, ld);
-                }
-            }
+            });
             if (lane < cnt) {  // one log per nonzero
                 tok_acc += (double)my_c * log(my_p);
                 cnt_acc += (double)my_c;

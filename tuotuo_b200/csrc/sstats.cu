@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsPa
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld;
+    const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
         const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsPa
             }
             const int64_t se = (we < ce) ? we : ce;  // segment [pos, se) of virtual word w
             KSlice<G, E> b, acc;
-            b.load(P.eB + (w % P.V) * P.ld, g, ld);
+            b.load(P.eB + (w % P.V) * P.ld, g, last_ok);
             acc.zero();
 
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
@@ -92,23 +93,11 @@ __global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsPa
                     my_d = ld_stream_s32(P.docidx + n0 + lane);
                     my_c = ld_stream_s32(P.ccounts + n0 + lane);
                 }
-                const int nsub = (cnt + R - 1) / R;
-                KSlice<G, E> cur, nxt;
-                cur.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, r) * P.ld, g, ld);
-                for (int s = 0; s < nsub; ++s) {
-                    const int i = s * R + r;
-                    if (PREFETCH && s + 1 < nsub)
-                        nxt.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, i + R) * P.ld, g, ld);
-                    const int cc = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt
-                    const double p = group_sum<G>(b.dot(cur));
-                    const double rr = (double)cc / (p + 1e-100);  // lda_model.py:242,262
-                    acc.axpy(rr, cur);
-                    if (PREFETCH) {
-                        cur = nxt;
-                    } else if (s + 1 < nsub) {
-                        cur.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, my_d, i + R) * P.ld, g, ld);
-                    }
-                }
+                walk_rows<G, E, PREFETCH>(P.eT, P.ld, my_d, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
+                    const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
+                    const double p = group_sum<G>(b.dot(row));
+                    acc.axpy((double)cc / (p + 1e-100), row);  // lda_model.py:242,262
+                });
             }
             // group partials -> one K-vector, written with coalesced stores
             acc.to_smem(wbuf + r * LDP, g);

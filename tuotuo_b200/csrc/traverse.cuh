@@ -21,14 +21,15 @@ template <int G, int E>
 struct KSlice {
     double2 v[E];
 
-    __device__ __forceinline__ void load(const double* __restrict__ row, int g, int ld)
+    // Slices j < E-1 are always inside the row (E is minimal for ld); only the last one needs a predicate, which is
+    // lane-constant (`last_ok`, see last_slice_ok) — so a load is E LDG.128 and nothing else.
+    __device__ __forceinline__ void load(const double* __restrict__ row, int g, bool last_ok)
     {
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            const int k = 2 * (g + G * j);
-            v[j] = (k < ld) ? ldg2(row + k) : make_double2(0., 0.);
-        }
+        for (int j = 0; j < E - 1; ++j) v[j] = ldg2(row + 2 * (g + G * j));
+        v[E - 1] = last_ok ? ldg2(row + 2 * (g + G * (E - 1))) : make_double2(0., 0.);
     }
+    static __device__ __forceinline__ bool last_slice_ok(int g, int ld) { return 2 * (g + G * (E - 1)) < ld; }
     __device__ __forceinline__ void zero()
     {
 #pragma unroll
@@ -60,6 +61,37 @@ struct KSlice {
         for (int j = 0; j < E; ++j) *reinterpret_cast<double2*>(row + 2 * (g + G * j)) = v[j];
     }
 };
+
+// Software-pipelined walk over the `cnt` (<= 32) rows whose indices the lanes hold in `my_idx` (lane i holds row
+// i): sub-batch s gives group r the row of lane s*R + r.  Two register buffers alternate (explicit ping-pong: no
+// register copies), the loads of sub-batch s+1 are issued before sub-batch s is consumed.
+// body(s, slice) is called once per sub-batch, warp-uniformly.
+template <int G, int E, bool PREFETCH, class Body>
+__device__ __forceinline__ void walk_rows(const double* __restrict__ table, int64_t ld64, int my_idx, int cnt, int g,
+                                          int r, bool last_ok, Body&& body)
+{
+    constexpr int R = 32 / G;
+    const int nsub = (cnt + R - 1) / R;
+    KSlice<G, E> A;
+    if (PREFETCH) {
+        KSlice<G, E> B;
+        A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, r) * ld64, g, last_ok);
+        int s = 0;
+        while (true) {
+            if (s + 1 < nsub) B.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+            body(s, A);
+            if (++s >= nsub) break;
+            if (s + 1 < nsub) A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+            body(s, B);
+            if (++s >= nsub) break;
+        }
+    } else {
+        for (int s = 0; s < nsub; ++s) {
+            A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, s * R + r) * ld64, g, last_ok);
+            body(s, A);
+        }
+    }
+}
 
 // sum over the G lanes of a group (result in every lane of the group)
 template <int G>
