@@ -113,8 +113,6 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
  *   gamma_in: the previous gamma [D][ld]; read only for the loop statistics (may be NULL iff iters_out is NULL,
  *   may alias gamma_out).  gamma_out / exp_elogtheta_out are written; exp_elogtheta_out must not alias the input
  *   (ping-pong), which lets a caller run the pass speculatively and discard it.
- *   sstats_atomic: if non-NULL, also scatters sstats[w,k] += eT_in[d,k]*c/N with red.global.add.f64 (the
- *   one-pass alternative to ttlda_sstats_csc_f64; not bit-reproducible).  Must be zeroed by the caller.
  *   partial_out double[TTLDA_NPART]: [0] token term at the incoming state, [1] theta-prior term at the outgoing
  *   state, [2] sum of counts.
  */
@@ -122,7 +120,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     int64_t D, int64_t K, int64_t V, int64_t ld,
                     const double* alpha_vec, double alpha_sum,
                     const double* exp_elogtheta_in, const double* exp_elogbeta,
-                    const double* gamma_in, double* gamma_out, double* exp_elogtheta_out, double* sstats_atomic,
+                    const double* gamma_in, double* gamma_out, double* exp_elogtheta_out,
                     int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -139,6 +137,13 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
                          int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks,
                          const double* exp_elogtheta, const double* exp_elogbeta, double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* One-pass alternative to ttlda_sstats_csc_f64 (the north-star's literal formulation): document-major scatter of
+ * eT[d,k]*c/N into sstats[w,k] with red.global.add.f64.  Same result up to summation order (NOT bit-reproducible);
+ * bounded by REDG throughput, kept for comparison.  sstats [V][ld] is zeroed by the call. */
+int ttlda_sstats_atomic_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                            int64_t D, int64_t K, int64_t V, int64_t ld,
+                            const double* exp_elogtheta, const double* exp_elogbeta, double* sstats, void* stream);
 
 /*
  * M-step: lambda = eta + sstats * exp_elogbeta;  exp_elogbeta <- exp(dirichlet_expectation(lambda));

@@ -24,7 +24,7 @@ def header_symbols():
 def test_header_declares_the_path():
     syms = header_symbols()
     for must in ["ttlda_dirichlet_expectation_f64", "ttlda_bow_to_csr", "ttlda_csr_to_csc", "ttlda_estep_f64",
-                 "ttlda_sstats_csc_f64", "ttlda_mstep_f64", "ttlda_elbo_tokens_f64", "ttlda_hyper_stats_f64",
+                 "ttlda_sstats_csc_f64", "ttlda_sstats_atomic_f64", "ttlda_mstep_f64", "ttlda_elbo_tokens_f64", "ttlda_hyper_stats_f64",
                  "ttlda_theta_refresh_f64", "ttlda_beta_refresh_f64", "ttlda_version", "ttlda_last_error"]:
         assert must in syms
 
@@ -52,7 +52,7 @@ def test_argument_validation_without_gpu(lib_path):
     from tuotuo_b200 import _native as nv
 
     lib = nv.load()
-    rc = lib.ttlda_estep_f64(None, None, None, 1, 5, 10, 8, None, 1.0, None, None, None, None, None, None, 1, 1e-5,
+    rc = lib.ttlda_estep_f64(None, None, None, 1, 5, 10, 8, None, 1.0, None, None, None, None, None, 1, 1e-5,
                              None, None, None, 0, None)
     assert rc == -1 and b"NULL" in lib.ttlda_last_error()
     rc = lib.ttlda_dirichlet_expectation_f64(None, 1, 1, 4, None, None, None)

@@ -192,10 +192,10 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1)
     nv.beta_refresh(lam, K, 1.0, eB, None, colsum, part[1], ws_m)
     nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, eT0, eB, part[2], ws)
     elbo0 = float(part[0, 0] + part[1, 0] + part[2, 0])
+    nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, 100, 1e-5, iters, part[3], ws)
     if mode == "atomic":
-        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, S, 100, 1e-5, iters, part[3], ws)
+        nv.sstats_atomic(c.rowptr, c.colidx, c.counts, K, V, eT0, eB, S)
     else:
-        nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, None, 100, 1e-5, iters, part[3], ws)
         nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, c.nblocks, eT0, eB, S, ws_s)
     upd = torch.empty((K, V), dtype=torch.float64, device=dev)
     nv.transpose_unpad(S * eB, K, upd)

@@ -12,7 +12,7 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libttlda.so")
+LIB_PATH = os.environ.get("TTLDA_LIB") or os.path.join(_PKG, "libttlda.so")  # TTLDA_LIB: tuning builds only
 
 NPART = 8
 MAX_K = 1024
@@ -37,7 +37,8 @@ SIGNATURES = {
     "ttlda_reduce_workspace_bytes": (_i64, []),
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
-                                       _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+                                       _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_sstats_atomic_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
                                             _i64, _ptr]),
@@ -66,7 +67,8 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
     "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2,
-    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_sstats_csc_f64": 2, "ttlda_mstep_f64": 4,
+    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1,
+    "ttlda_mstep_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
 }
@@ -189,13 +191,12 @@ def theta_refresh(gamma, K, alpha_vec, alpha_sum, eT, partial, ws):
           _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
-def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out, sstats_atomic,
+def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out,
           max_iter, tol, iters, partial, ws):
     D, ld = gamma_out.shape
     _call("ttlda_estep_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
           _p(alpha_vec, f64), float(alpha_sum), _p(eT_in, f64), _p(eB, f64), _p(gamma_in, f64), _p(gamma_out, f64),
-          _p(eT_out, f64),
-          _p(sstats_atomic, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
+          _p(eT_out, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
           ws.numel() * ws.element_size(), _stream())
 
 
@@ -209,6 +210,12 @@ def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws):
     kernel_count += 1 if nblocks > 1 else 0  # + sstats_fold_kernel
     _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), int(V), int(K), ld, int(nnz),
           int(nblocks), _p(eT, f64), _p(eB, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def sstats_atomic(rowptr, colidx, counts, K, V, eT, eB, sstats):
+    D, ld = eT.shape
+    _call("ttlda_sstats_atomic_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
+          _p(eT, f64), _p(eB, f64), _p(sstats, f64), _stream())
 
 
 def mstep_workspace_bytes(V, ld) -> int:

@@ -34,7 +34,6 @@ struct EStepParams {
     const double* gamma_in;  // previous gamma (only read for the loop statistics), may be NULL
     double* gamma_out;
     double* eT_out;
-    double* sstats_atomic;
     int64_t max_iter;
     double tol;
     unsigned long long* iters;  // [2] device counters (passes, capped docs) or NULL
@@ -44,7 +43,7 @@ struct EStepParams {
 constexpr int kDocThreads = 128;  // 4 warps per CTA
 
 template <int G, int E, bool PREFETCH, bool ESTEP>
-__global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams P)
+__global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel(const EStepParams P)
 {
     constexpr int R = 32 / G;
     constexpr int LDP = 2 * G * E;
@@ -75,12 +74,20 @@ __global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams
         t.load(P.eT_in + d * P.ld, g, last_ok);
         acc.zero();
 
+        // (word, count) pairs: 32 per coalesced load, fetched ONE batch ahead so that their latency is hidden
+        int nx_w = 0, nx_c = 0;
+        if (b + lane < e) {
+            nx_w = ld_stream_s32(P.colidx + b + lane);
+            nx_c = ld_stream_s32(P.counts + b + lane);
+        }
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
-            int my_w = 0, my_c = 0;
-            if (lane < cnt) {
-                my_w = ld_stream_s32(P.colidx + n0 + lane);
-                my_c = ld_stream_s32(P.counts + n0 + lane);
+            const int my_w = nx_w, my_c = nx_c;
+            nx_w = 0;
+            nx_c = 0;
+            if (n0 + 32 + lane < e) {
+                nx_w = ld_stream_s32(P.colidx + n0 + 32 + lane);
+                nx_c = ld_stream_s32(P.counts + n0 + 32 + lane);
             }
             double my_p = 1.;
             walk_rows<G, E, PREFETCH>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
@@ -90,18 +97,6 @@ __global__ void __launch_bounds__(kDocThreads) doc_pass_kernel(const EStepParams
                 if (ESTEP) {
                     const double rr = (double)c / (p + 1e-100);
                     acc.axpy(rr, row);
-                    if (P.sstats_atomic) {  // warp-uniform branch
-                        const int wi = __shfl_sync(0xffffffffu, my_w, i);
-                        if (c) {
-                            double* srow = P.sstats_atomic + (int64_t)wi * P.ld;
-#pragma unroll
-                            for (int j = 0; j < E; ++j) {
-                                const int k = 2 * (g + G * j);
-                                if (k < K) atomicAdd(srow + k, t.v[j].x * rr);
-                                if (k + 1 < K) atomicAdd(srow + k + 1, t.v[j].y * rr);
-                            }
-                        }
-                    }
                 }
                 // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
@@ -218,7 +213,7 @@ extern "C" {
 int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t K,
                     int64_t V, int64_t ld, const double* alpha_vec, double alpha_sum,
                     const double* exp_elogtheta_in, const double* exp_elogbeta, const double* gamma_in,
-                    double* gamma_out, double* exp_elogtheta_out, double* sstats_atomic, int64_t max_iter, double tol,
+                    double* gamma_out, double* exp_elogtheta_out, int64_t max_iter, double tol,
                     int64_t* iters_out, double* partial_out, void* workspace, int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma_out && exp_elogtheta_out &&
@@ -239,7 +234,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
         if (e != cudaSuccess) return cuda_fail(e, "memset iters");
     }
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta_in, exp_elogbeta,
-                  gamma_in, gamma_out, exp_elogtheta_out, sstats_atomic, max_iter, tol,
+                  gamma_in, gamma_out, exp_elogtheta_out, max_iter, tol,
                   (unsigned long long*)iters_out, (double*)workspace};
     int rc = launch_doc_pass<true>(P, s);
     if (rc != TTLDA_OK) return rc;
@@ -260,7 +255,7 @@ int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const in
     }
     cudaStream_t s = (cudaStream_t)stream;
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, nullptr, 0., exp_elogtheta, exp_elogbeta,
-                  nullptr, nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
+                  nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
     int rc = launch_doc_pass<false>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("elbo_tokens");

@@ -45,7 +45,7 @@ struct SStatsParams {
 };
 
 template <int G, int E, bool PREFETCH>
-__global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsParams P)
+__global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_kernel(const SStatsParams P)
 {
     constexpr int R = 32 / G;
     constexpr int LDP = 2 * G * E;
@@ -86,12 +86,20 @@ __global__ void __launch_bounds__(kWordThreads) sstats_csc_kernel(const SStatsPa
             b.load(P.eB + (w % P.V) * P.ld, g, last_ok);
             acc.zero();
 
+            // (document, count) pairs: 32 per coalesced load, fetched ONE batch ahead
+            int nx_d = 0, nx_c = 0;
+            if (pos + lane < se) {
+                nx_d = ld_stream_s32(P.docidx + pos + lane);
+                nx_c = ld_stream_s32(P.ccounts + pos + lane);
+            }
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
-                int my_d = 0, my_c = 0;
-                if (lane < cnt) {
-                    my_d = ld_stream_s32(P.docidx + n0 + lane);
-                    my_c = ld_stream_s32(P.ccounts + n0 + lane);
+                const int my_d = nx_d, my_c = nx_c;
+                nx_d = 0;
+                nx_c = 0;
+                if (n0 + 32 + lane < se) {
+                    nx_d = ld_stream_s32(P.docidx + n0 + 32 + lane);
+                    nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane);
                 }
                 walk_rows<G, E, PREFETCH>(P.eT, P.ld, my_d, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
                     const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
@@ -170,6 +178,32 @@ static void launch_shape(const SStatsParams& P, int grid, cudaStream_t s)
     sstats_csc_kernel<G, E, PF><<<grid, kWordThreads, smem, s>>>(P);
 }
 
+// One-pass alternative (the north-star's literal formulation): document-major scatter with red.global.add.f64.
+// One warp per document, lane l owns topics l, l+32, ...; the normaliser is recomputed per nonzero.  Kept for
+// comparison: REDG throughput bounds it well below the two-pass form, and the sums are not bit-reproducible.
+__global__ void __launch_bounds__(256) sstats_atomic_kernel(const int64_t* __restrict__ rowptr,
+                                                            const int32_t* __restrict__ colidx,
+                                                            const int32_t* __restrict__ counts, int64_t D, int K,
+                                                            int64_t ld, const double* __restrict__ eT,
+                                                            const double* __restrict__ eB, double* __restrict__ S)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = warp0; d < D; d += nwarps) {
+        const double* t = eT + d * ld;
+        for (int64_t n = rowptr[d]; n < rowptr[d + 1]; ++n) {
+            const int64_t w = colidx[n];
+            const double* b = eB + w * ld;
+            double p = 0.;
+            for (int k = lane; k < K; k += 32) p = fma(t[k], b[k], p);
+            p = warp_sum(p);
+            const double rr = (double)counts[n] / (p + 1e-100);  // lda_model.py:242,262
+            for (int k = lane; k < K; k += 32) atomicAdd(S + w * ld + k, t[k] * rr);
+        }
+    }
+}
+
 }  // namespace ttlda
 
 using namespace ttlda;
@@ -245,6 +279,23 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
         sstats_fold_kernel<<<fg, 256, 0, s>>>(Sb, V, ld, (int)nblocks, sstats);
         TTLDA_LAUNCH_CHECK("sstats_fold");
     }
+    return TTLDA_OK;
+}
+
+int ttlda_sstats_atomic_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t K,
+                            int64_t V, int64_t ld, const double* exp_elogtheta, const double* exp_elogbeta,
+                            double* sstats, void* stream)
+{
+    TTLDA_REQUIRE(rowptr && exp_elogtheta && exp_elogbeta && sstats, "NULL pointer");
+    TTLDA_REQUIRE(D >= 0 && V >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
+    TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(sstats, 0, (size_t)V * ld * sizeof(double), s);
+    if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
+    if (D == 0) return TTLDA_OK;
+    sstats_atomic_kernel<<<grid_for_warps(D, 8, 8), 256, 0, s>>>(rowptr, colidx, counts, D, (int)K, ld, exp_elogtheta,
+                                                                exp_elogbeta, sstats);
+    TTLDA_LAUNCH_CHECK("sstats_atomic");
     return TTLDA_OK;
 }
 

@@ -38,13 +38,18 @@ struct KSlice {
     // partial dot product over this lane's slices
     __device__ __forceinline__ double dot(const KSlice& o) const
     {
-        double p0 = 0., p1 = 0.;
+        double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;  // four independent DFMA chains
 #pragma unroll
         for (int j = 0; j < E; ++j) {
-            p0 = fma(v[j].x, o.v[j].x, p0);
-            p1 = fma(v[j].y, o.v[j].y, p1);
+            if (j & 1) {
+                p2 = fma(v[j].x, o.v[j].x, p2);
+                p3 = fma(v[j].y, o.v[j].y, p3);
+            } else {
+                p0 = fma(v[j].x, o.v[j].x, p0);
+                p1 = fma(v[j].y, o.v[j].y, p1);
+            }
         }
-        return p0 + p1;
+        return (p0 + p1) + (p2 + p3);
     }
     __device__ __forceinline__ void axpy(double a, const KSlice& x)
     {
@@ -121,8 +126,8 @@ inline GroupShape group_shape_for(int64_t ld)
     X(2, 1) X(2, 2) X(2, 3) X(2, 4) X(2, 5) X(2, 6) X(2, 7) X(2, 8)                                   \
     X(4, 5) X(4, 6) X(4, 7) X(4, 8)                                                                   \
     X(8, 5) X(8, 6) X(8, 7) X(8, 8)                                                                   \
-    X(16, 4) X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                                      \
-    X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8) X(32, 9) X(32, 10) X(32, 11) X(32, 12) X(32, 13) X(32, 14) \
+    X(16, 2) X(16, 3) X(16, 4) X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                    \
+    X(32, 2) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8) X(32, 9) X(32, 10) X(32, 11) X(32, 12) X(32, 13) X(32, 14) \
     X(32, 15) X(32, 16)
 
 }  // namespace ttlda

@@ -231,18 +231,16 @@ class LDASmoothed:
         token term of the CURRENT state (part[0][0]), which completes its perplexity."""
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
-        atomic = self._sstats_mode == "atomic"
-        if atomic:
-            st.sstats.zero_()
         nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], st.sstats if atomic else None, e_num_step, e_threshold,
-                 st.iters, st.part[0], st.ws)
+                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws)
 
     def _commit_iteration(self):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
         adopt the E-step's gamma / exp(E[log theta])."""
         st, c = self._st, self._st.corpus
-        if self._sstats_mode != "atomic":
+        if self._sstats_mode == "atomic":
+            nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, st.eT[st.cur], st.eB, st.sstats)
+        else:
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[st.cur], st.eB, st.sstats,
                           st.ws_s)
         dist = self._dist()
@@ -499,7 +497,7 @@ class LDASmoothed:
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
         nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], None, step, threshold, st.iters, st.part[0], st.ws)
+                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], step, threshold, st.iters, st.part[0], st.ws)
         c.ensure_csc(st.ld)
         ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, st.V, st.ld, c.nblocks), dtype=torch.uint8, device=st.dev)
         nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[cur], st.eB, st.sstats, ws_s)
