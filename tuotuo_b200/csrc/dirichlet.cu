@@ -99,20 +99,23 @@ __global__ void __launch_bounds__(256) theta_refresh_kernel(const double* __rest
         double s = 0.;
         for (int k = lane; k < K; k += 32) s += g[k];
         s = warp_sum(s);
-        const double pt = psi_as103(s);
+        double pt, lg_s;
+        psi_lgamma_as103(s, pt, lg_s);
         double t = 0.;
         for (int k = lane; k < (int)ld; k += 32) {
             if (k < K) {
                 const double gk = g[k];
-                const double e = psi_as103(gk) - pt;
-                t += (alpha_vec[k] - gk) * e + lgamma(gk);
+                double ps, lg;
+                psi_lgamma_as103(gk, ps, lg);
+                const double e = ps - pt;
+                t += (alpha_vec[k] - gk) * e + lg;
                 if (eT) eT[d * ld + k] = exp(e);
             } else if (eT) {
                 eT[d * ld + k] = 0.;
             }
         }
         t = warp_sum(t);
-        term += t - lga + (lg_asum - lgamma(s));
+        term += t - lga + (lg_asum - lg_s);
     }
     double v[1] = {lane == 0 ? term : 0.};
     block_sum<1>(v, sm);

@@ -137,14 +137,17 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 passes += np;
                 capped += ((int64_t)np > P.max_iter) ? 1ull : 0ull;
             }
-            const double pt = psi_as103(s);
+            double pt, lg_s;
+            psi_lgamma_as103(s, pt, lg_s);
             double th = 0.;
 #pragma unroll
             for (int m = 0; m < MMAX; ++m) {
                 const int k = lane + 32 * m;
                 if (k < K) {
-                    const double el = psi_as103(gn[m]) - pt;
-                    th += (P.alpha_vec[k] - gn[m]) * el + lgamma(gn[m]);
+                    double ps, lg;
+                    psi_lgamma_as103(gn[m], ps, lg);
+                    const double el = ps - pt;
+                    th += (P.alpha_vec[k] - gn[m]) * el + lg;
                     P.gamma_out[d * P.ld + k] = gn[m];
                     P.eT_out[d * P.ld + k] = exp(el);
                 }
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 P.eT_out[d * P.ld + K + lane] = 0.;
             }
             th = warp_sum(th);
-            theta_acc += th - lga + (lg_asum - lgamma(s));
+            theta_acc += th - lga + (lg_asum - lg_s);
         }
     }
 

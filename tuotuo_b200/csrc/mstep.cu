@@ -102,9 +102,11 @@ __global__ void __launch_bounds__(256) beta_refresh_kernel(const double* __restr
         double e = 0., x = 0.;
         if (k < K) {
             const double lam = lambda[i];
-            e = psi_as103(lam) - psi_colsum[k];        // cutils.pyx:65-66
+            double ps, lg;
+            psi_lgamma_as103(lam, ps, lg);
+            e = ps - psi_colsum[k];                    // cutils.pyx:65-66
             x = exp(e);
-            t[0] += (eta - lam) * e + (lgamma(lam) - lg_eta);  // lda_model.py:40-41
+            t[0] += (eta - lam) * e + (lg - lg_eta);  // lda_model.py:40-41
         }
         eB[i] = x;
         if (elogbeta) elogbeta[i] = e;

@@ -84,6 +84,38 @@ __device__ __forceinline__ double psi_as103(double x)
     return result;
 }
 
+// Fused AS-103 digamma + log-gamma for the ELBO prior terms (the reference evaluates psi~(x) in cutils.pyx:75-93 and
+// scipy.special.gammaln(x) in lda_model.py:41 separately).  Both need the same upward shift to x >= 6, log(x) and
+// 1/x, so they are evaluated together:
+//   * the AS-103 recurrence  result -= 1/x  (one IEEE division per step, up to six steps for the many gamma_dk ~ 1)
+//     is folded into ONE division: sum_i 1/(x+i) = q/p with p = prod_i (x+i), q accumulated by FMA — same value to
+//     ~1e-16 relative (parity needs 1e-9), ~5x fewer instructions;
+//   * lgamma(x) = Stirling(x_shifted) - log(p), series through x^-13 (|err| < 6e-14 absolute for x_shifted >= 6).
+__device__ __forceinline__ void psi_lgamma_as103(double x, double& psi_out, double& lgam_out)
+{
+    if (x <= 1e-6) {  // cutils.pyx:76-78
+        psi_out = -0.577215664901532860606512090082402431 - 1. / x;
+        lgam_out = lgamma(x);
+        return;
+    }
+    double p = 1., q = 0.;
+    while (x < 6.) {  // cutils.pyx:83-85
+        q = fma(q, x, p);
+        p *= x;
+        x += 1.;
+    }
+    const double r = 1. / x, lx = log(x), r2 = r * r;  // cutils.pyx:89-92
+    double res = lx - .5 * r;
+    res -= r2 * ((1. / 12.) - r2 * ((1. / 120.) - r2 * (1. / 252.)));
+    psi_out = res - q / p;
+    const double series =
+        r * ((1. / 12.) -
+             r2 * ((1. / 360.) -
+                   r2 * ((1. / 1260.) -
+                         r2 * ((1. / 1680.) - r2 * ((1. / 1188.) - r2 * ((691. / 360360.) - r2 * (1. / 156.)))))));
+    lgam_out = (x - .5) * lx - x + 0.91893853320467274178 + series - log(p);
+}
+
 // Exact digamma for x > 0 (recurrence to x >= 10, then the asymptotic series through x^-14; |err| ~ 1e-16
 // relative).  Used only where the reference calls scipy.special.psi (hyper-parameter Newton updates).
 __device__ __forceinline__ double psi_exact(double x)
