@@ -137,7 +137,12 @@ def version() -> int:
     return int(load().ttlda_version())
 
 
-def check_device(device: int = 0) -> None:
+def check_device(device=0) -> None:
+    """Raise unless `device` (index or torch.device) is an sm_100 GPU."""
+    if isinstance(device, torch.device):
+        if device.type != "cuda":
+            raise TTLDAError(f"libttlda needs a CUDA device, got {device} (there is no CPU fallback)")
+        device = device.index if device.index is not None else torch.cuda.current_device()
     _check(load().ttlda_check_device(int(device)), "ttlda_check_device")
 
 

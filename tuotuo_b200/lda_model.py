@@ -118,7 +118,7 @@ class LDASmoothed:
 
     def _alloc_state(self, corpus: DeviceCorpus):
         dev = corpus.device
-        nv.check_device(dev.index if dev.index is not None else torch.cuda.current_device())
+        nv.check_device(dev)
         K, V, D = int(self.K), corpus.V, corpus.D
         if not 1 <= K <= nv.MAX_K:
             raise ValueError(f"num_topics must be in [1, {nv.MAX_K}]")
