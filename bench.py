@@ -40,12 +40,13 @@ UNIT = "doc-tokens/s"
 def algorithmic_bytes(nnz, D, K, V):
     """Gather-model bytes.  Per launch of each kernel and per EM iteration."""
     kb = 8 * K
-    est = nnz * (kb + 8) + D * kb * 5 + (D + 1) * 8      # gather eB row + (colidx,count); eT in x2, gamma in/out, eT out
+    est = nnz * (kb + 8) + D * kb * 4 + (D + 1) * 8      # gather eB row + (colidx,count); eT in x2, gamma in/out
+    ref = D * kb * 2                                       # theta refresh pass: gamma in, eT out
     sst = nnz * (kb + 8) + V * kb * 2 + (V + 1) * 8      # gather eT row + (docidx,count); eB in, S out
     mst = V * kb * 6                                       # S, eB in; lambda out; lambda in; eB out (+colsum pass)
     # the ELBO token term is a by-product of the E-step (same dot product): no third gather => 16K bytes per nonzero
     return {"ttlda_estep_f64": est, "ttlda_sstats_csc_f64": sst, "ttlda_mstep_f64": mst,
-            "iteration": est + sst + mst}
+            "ttlda_theta_refresh_f64": ref, "iteration": est + sst + mst + ref}
 
 
 def measured_peaks():

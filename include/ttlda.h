@@ -110,6 +110,9 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
  * update is idempotent and the loop exits on its second pass; the kernel evaluates the update once and reports
  * `iters_out[0]` = sum over documents of the passes the reference would have made, `iters_out[1]` = documents
  * that hit the cap (`it > max_iter`, warned about at :258-259).
+ *   exp_elogtheta_out may be NULL: then only gamma_out is written and partial_out[1] = 0 — run
+ *   ttlda_theta_refresh_f64 on gamma_out afterwards (same results; the refresh's digamma/log-gamma/exp chains then
+ *   run as a separate fully parallel pass instead of on the critical path of the per-document warps).
  *   gamma_in: the previous gamma [D][ld]; read only for the loop statistics (may be NULL iff iters_out is NULL,
  *   may alias gamma_out).  gamma_out / exp_elogtheta_out are written; exp_elogtheta_out must not alias the input
  *   (ping-pong), which lets a caller run the pass speculatively and discard it.

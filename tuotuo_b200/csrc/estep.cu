@@ -42,9 +42,13 @@ struct EStepParams {
 
 constexpr int kDocThreads = 128;  // 4 warps per CTA
 
-template <int G, int E, bool PREFETCH, bool ESTEP>
+// MODE 0: ELBO token term only;  1: E-step with the theta refresh + theta-prior term fused into the per-document
+// epilogue;  2: E-step writing gamma only (the refresh is then run as the separate, fully parallel theta_refresh pass:
+// the epilogue's digamma/log-gamma/exp chains otherwise sit on the critical path of a warp that has nothing else to do)
+template <int G, int E, bool PREFETCH, int MODE>
 __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel(const EStepParams P)
 {
+    constexpr bool ESTEP = MODE > 0, REFRESH = MODE == 1;
     constexpr int R = 32 / G;
     constexpr int LDP = 2 * G * E;
     constexpr int MMAX = (LDP + 31) / 32;
@@ -60,7 +64,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
 
     double lga = 0., lg_asum = 0.;
-    if (ESTEP) {
+    if (REFRESH) {
         for (int k = lane; k < K; k += 32) lga += lgamma(P.alpha_vec[k]);
         lga = warp_sum(lga);
         lg_asum = lgamma(P.alpha_sum);
@@ -137,27 +141,36 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 passes += np;
                 capped += ((int64_t)np > P.max_iter) ? 1ull : 0ull;
             }
-            double pt, lg_s;
-            psi_lgamma_as103(s, pt, lg_s);
-            double th = 0.;
+            if (REFRESH) {
+                double pt, lg_s;
+                psi_lgamma_as103(s, pt, lg_s);
+                double th = 0.;
 #pragma unroll
-            for (int m = 0; m < MMAX; ++m) {
-                const int k = lane + 32 * m;
-                if (k < K) {
-                    double ps, lg;
-                    psi_lgamma_as103(gn[m], ps, lg);
-                    const double el = ps - pt;
-                    th += (P.alpha_vec[k] - gn[m]) * el + lg;
-                    P.gamma_out[d * P.ld + k] = gn[m];
-                    P.eT_out[d * P.ld + k] = exp(el);
+                for (int m = 0; m < MMAX; ++m) {
+                    const int k = lane + 32 * m;
+                    if (k < K) {
+                        double ps, lg;
+                        psi_lgamma_as103(gn[m], ps, lg);
+                        const double el = ps - pt;
+                        th += (P.alpha_vec[k] - gn[m]) * el + lg;
+                        P.gamma_out[d * P.ld + k] = gn[m];
+                        P.eT_out[d * P.ld + k] = exp(el);
+                    }
                 }
+                if (lane < ld - K) {  // padding columns
+                    P.gamma_out[d * P.ld + K + lane] = 0.;
+                    P.eT_out[d * P.ld + K + lane] = 0.;
+                }
+                th = warp_sum(th);
+                theta_acc += th - lga + (lg_asum - lg_s);
+            } else {
+#pragma unroll
+                for (int m = 0; m < MMAX; ++m) {
+                    const int k = lane + 32 * m;
+                    if (k < K) P.gamma_out[d * P.ld + k] = gn[m];
+                }
+                if (lane < ld - K) P.gamma_out[d * P.ld + K + lane] = 0.;
             }
-            if (lane < ld - K) {  // padding columns
-                P.gamma_out[d * P.ld + K + lane] = 0.;
-                P.eT_out[d * P.ld + K + lane] = 0.;
-            }
-            th = warp_sum(th);
-            theta_acc += th - lga + (lg_asum - lg_s);
         }
     }
 
@@ -177,17 +190,17 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
     }
 }
 
-template <int G, int E, bool ESTEP>
+template <int G, int E, int MODE>
 static int launch_shape(const EStepParams& P, int grid, cudaStream_t s)
 {
     constexpr int R = 32 / G;
     constexpr size_t smem = (96 + (kDocThreads / 32) * R * 2 * G * E) * sizeof(double);
     constexpr bool PF = (E <= 8);  // register budget: t, acc, cur, nxt = 8E doubles
-    doc_pass_kernel<G, E, PF, ESTEP><<<grid, kDocThreads, smem, s>>>(P);
+    doc_pass_kernel<G, E, PF, MODE><<<grid, kDocThreads, smem, s>>>(P);
     return TTLDA_OK;
 }
 
-template <bool ESTEP>
+template <int MODE>
 static int launch_doc_pass(const EStepParams& P, cudaStream_t s)
 {
     GroupShape gs = group_shape_for(P.ld);
@@ -200,7 +213,7 @@ static int launch_doc_pass(const EStepParams& P, cudaStream_t s)
     }
     const int grid = grid_for_warps(P.D, kDocThreads / 32, 16);
 #define TTLDA_CASE(GG, EE) \
-    if (gs.G == GG && gs.E == EE) return launch_shape<GG, EE, ESTEP>(P, grid, s);
+    if (gs.G == GG && gs.E == EE) return launch_shape<GG, EE, MODE>(P, grid, s);
     TTLDA_FOR_EACH_SHAPE(TTLDA_CASE)
 #undef TTLDA_CASE
     set_error("no kernel instantiated for ld=%lld (G=%d, E=%d)", (long long)P.ld, gs.G, gs.E);
@@ -219,8 +232,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     double* gamma_out, double* exp_elogtheta_out, int64_t max_iter, double tol,
                     int64_t* iters_out, double* partial_out, void* workspace, int64_t workspace_bytes, void* stream)
 {
-    TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma_out && exp_elogtheta_out &&
-                      partial_out && workspace,
+    TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma_out && partial_out && workspace,
                   "NULL pointer");
     TTLDA_REQUIRE(D >= 0 && V >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
     TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
@@ -239,7 +251,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta_in, exp_elogbeta,
                   gamma_in, gamma_out, exp_elogtheta_out, max_iter, tol,
                   (unsigned long long*)iters_out, (double*)workspace};
-    int rc = launch_doc_pass<true>(P, s);
+    int rc = exp_elogtheta_out ? launch_doc_pass<1>(P, s) : launch_doc_pass<2>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("estep");
     return launch_reduce_records((const double*)workspace, grid_for_warps(D, kDocThreads / 32, 16), partial_out, s);
@@ -259,7 +271,7 @@ int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const in
     cudaStream_t s = (cudaStream_t)stream;
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, nullptr, 0., exp_elogtheta, exp_elogbeta,
                   nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
-    int rc = launch_doc_pass<false>(P, s);
+    int rc = launch_doc_pass<0>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("elbo_tokens");
     return launch_reduce_records((const double*)workspace, grid_for_warps(D, kDocThreads / 32, 16), partial_out, s);

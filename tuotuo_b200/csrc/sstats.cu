@@ -62,11 +62,19 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
         const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
-        // first virtual word with colptr[w+1] > cb
-        int64_t lo = 0, hi = P.VV;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (P.colptr[mid + 1] > cb) hi = mid; else lo = mid + 1;
+        // first virtual word with colptr[w+1] > cb: warp-cooperative 32-ary search (4 dependent loads for 10^6 words
+        // instead of 20 — the chunk's start-up latency is not hidden by anything else in this warp)
+        int64_t lo = 0, hi = P.VV;  // the answer lies in [lo, hi); colptr[VV] = nnz > cb
+        while (hi - lo > 1) {
+            const int64_t step = (hi - lo + 31) >> 5;
+            int64_t wi = lo + (int64_t)(lane + 1) * step - 1;
+            if (wi > hi - 1) wi = hi - 1;
+            const unsigned hit = __ballot_sync(0xffffffffu, P.colptr[wi + 1] > cb);  // monotone: 0..0 1..1
+            const int j = __ffs(hit) - 1;                                            // lane 31 probes hi-1 => hit != 0
+            const int64_t wj = lo + (int64_t)(j + 1) * step - 1;
+            const int64_t new_hi = ((wj > hi - 1) ? hi - 1 : wj) + 1;
+            if (j > 0) lo = lo + (int64_t)j * step;  // = w_{j-1} + 1
+            hi = new_hi;
         }
         int64_t w = lo;
         if (lane == 0) {

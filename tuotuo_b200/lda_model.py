@@ -20,6 +20,7 @@ After the last iteration one ttlda_elbo_tokens_f64 pass yields the final perplex
 """
 from __future__ import annotations
 
+import os
 import warnings
 
 import numpy as np
@@ -71,6 +72,7 @@ class LDASmoothed:
         if sstats_mode not in ("csc", "atomic"):
             raise ValueError("sstats_mode must be 'csc' (two-pass, reproducible) or 'atomic' (one pass, red.f64)")
         self._sstats_mode = sstats_mode
+        self._fused_refresh = os.environ.get("TTLDA_FUSED_REFRESH", "0") == "1"
         self._device = device
         self._st = None
         self._np_cache = {}
@@ -231,8 +233,15 @@ class LDASmoothed:
         token term of the CURRENT state (part[0][0]), which completes its perplexity."""
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
-        nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws)
+        if self._fused_refresh:
+            nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
+                     st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws)
+        else:
+            # gamma only; the theta refresh (digamma / log-gamma / exp per gamma_dk) runs as its own streaming pass
+            nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
+                     st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws)
+            nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
+            st.part[0, 1].copy_(st.part[4, 0])
 
     def _commit_iteration(self):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
