@@ -128,6 +128,22 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * OPT-IN E-step with a true per-document fixed point (not the reference's behaviour — SURVEY.md §8f row 1):
+ * exp(E[log theta_d]) is refreshed after every gamma_d update inside the reference's loop
+ * (`while l1 > tol and it <= max_iter`, tuotuo/lda_model.py:236) instead of being frozen, as in Blei/Hoffman and
+ * scikit-learn's _update_doc_distribution.  Same arguments as ttlda_estep_f64 (all required, outputs must not alias
+ * inputs).  iters_out[0] = total inner iterations, iters_out[1] = documents that hit the cap.  The statistics pass
+ * must then be given exp_elogtheta_out (the refreshed table), which re-evaluates the normaliser with the final theta.
+ */
+int ttlda_estep_fixed_point_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
+                                int64_t D, int64_t K, int64_t V, int64_t ld,
+                                const double* alpha_vec, double alpha_sum,
+                                const double* exp_elogtheta_in, const double* exp_elogbeta,
+                                const double* gamma_in, double* gamma_out, double* exp_elogtheta_out,
+                                int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
+                                void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * M-step sufficient statistics, word-major pass over the CSC mirror (no atomics, no phi in HBM):
  *      sstats[w,k] = sum_{d: X_dw>0} eT[d,k] * c_dw / (sum_k' eT[d,k'] eB[w,k'] + 1e-100)
  * Replaces: lambda_update[:, ids] += np.outer(eT, cts/phi_norm) at tuotuo/lda_model.py:262 (the trailing

@@ -73,7 +73,7 @@ def _lib():
         lib.ttor_dirichlet_expectation_1d.argtypes = [dp, ctypes.c_double, dp, i64]
         lib.ttor_e_step.restype = i64
         lib.ttor_e_step.argtypes = [i64p, i32p, i32p, i64, i64, i64, dp, dp, dp, dp, dp, dp, i64,
-                                    ctypes.c_double, i64p]
+                                    ctypes.c_double, i64p, ctypes.c_int]
         lib.ttor_m_step.restype = None
         lib.ttor_m_step.argtypes = [dp, ctypes.c_double, i64, i64, dp, dp]
         lib.ttor_elbo.restype = ctypes.c_double
@@ -241,6 +241,7 @@ class OracleLDA:
     K: int
     exchangeable_prior: bool = True
     engine: str = "c"
+    inner_fixed_point: bool = False  # NOT the reference: restates the CUDA library's opt-in true-fixed-point mode
     alpha: object = field(init=False)
     eta: object = field(init=False)
 
@@ -329,7 +330,8 @@ class OracleLDA:
                 _p(X.rowptr, ctypes.c_int64), _p(X.colidx, ctypes.c_int32), _p(X.counts, ctypes.c_int32),
                 D, K, V, _p(av, ctypes.c_double), _p(np.ascontiguousarray(Elogtheta), ctypes.c_double),
                 _p(eB, ctypes.c_double), _p(self.gamma, ctypes.c_double), _p(S, ctypes.c_double),
-                _p(Et_out, ctypes.c_double), int(step), float(threshold), ctypes.byref(iters))
+                _p(Et_out, ctypes.c_double), int(step), float(threshold), ctypes.byref(iters),
+                int(self.inner_fixed_point))
             self.inner_iters += iters.value
             self.capped_docs += int(capped)
             return self.gamma, (S, Et_out)
@@ -347,7 +349,11 @@ class OracleLDA:
                 norm = np.dot(eT.T, eB) + 1e-100  # :242
                 self.gamma[d, :] = (self.alpha + eT.T * np.dot(cts.T / norm, eB.T)).ravel()  # :248
                 l1 = np.linalg.norm(self.gamma[d] - g_old, ord=1)
+                if self.inner_fixed_point:  # opt-in mode only: refresh exp(E[log theta_d]) inside the loop
+                    eT = np.exp(dirichlet_expectation_2d(self.gamma[d:d + 1], "numpy")).T
                 it += 1
+            if self.inner_fixed_point:
+                norm = np.dot(eT.T, eB) + 1e-100
             self.inner_iters += it
             if it > step:
                 self.capped_docs += 1

@@ -115,14 +115,15 @@ def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_i
         _np(iters)[1] = int((passes > max_iter).sum())
     _np(gamma_out)[:] = 0.0
     _np(gamma_out)[:, :K] = g_new
-    E = orc.dirichlet_expectation_2d(g_new) if g_new.shape[0] else g_new
-    _np(eT_out)[:] = 0.0
-    _np(eT_out)[:, :K] = np.exp(E)
     p = _np(partial)
     p[:] = 0.0
     p[0] = float(np.sum(c * np.log(dot)))
-    p[1] = _theta_term(g_new, E, a, alpha_sum)
     p[2] = float(c.sum())
+    if eT_out is not None:  # fused theta refresh; otherwise the driver runs theta_refresh itself
+        E = orc.dirichlet_expectation_2d(g_new) if g_new.shape[0] else g_new
+        _np(eT_out)[:] = 0.0
+        _np(eT_out)[:, :K] = np.exp(E)
+        p[1] = _theta_term(g_new, E, a, alpha_sum)
 
 
 def elbo_tokens(rowptr, colidx, counts, K, eT, eB, partial, ws):

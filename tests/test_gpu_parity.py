@@ -407,3 +407,25 @@ def test_every_group_width_is_exact(monkeypatch, G, K):
     m = LDASmoothed(K, verbose=False)
     pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, return_perplexities=True)
     assert relerr(pg, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+
+
+@pytest.mark.parametrize("K,V,D,L", [(10, 300, 120, 50), (100, 1200, 150, 90), (300, 900, 40, 120), (1000, 1100, 12, 100)])
+def test_inner_fixed_point_mode_vs_oracle(K, V, D, L):
+    """Opt-in true fixed point (NOT the reference's behaviour): exp(E[log theta_d]) refreshed inside the
+    per-document loop until ||dgamma||_1 <= 1e-5.  Checked against the oracle's restatement of the same mode."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(900 + K, D, V, min(K, 25), L, ragged=True)
+    o = OracleLDA(K, engine="c", inner_fixed_point=True)
+    po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=3)
+    m = LDASmoothed(K, verbose=False, inner_fixed_point=True)
+    pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert o.inner_iters > 4 * 3 * D  # the loop really iterates (the frozen-theta reference makes 2 passes)
+    assert relerr(m._last_elbo, o.last_elbo) < 1e-10 and relerr(pg, po) < TOL_PERP
+    assert relerr(m._gamma_, o.gamma) < 1e-8 and relerr(m._lambda_, o.lam) < 1e-8
+    # and it is a different (better-converged) answer than the reference-parity mode
+    ref = LDASmoothed(K, verbose=False)
+    pr = ref.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    assert pg[3] < pr[3]

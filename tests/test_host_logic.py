@@ -123,3 +123,21 @@ def test_lda_constructor_prints_and_priors(capsys):
     np.testing.assert_array_equal(m2._alpha_, np.random.gamma(shape=100, scale=0.01, size=(1, 6)))
     with pytest.raises(AttributeError):
         m._lambda_
+
+
+def test_uci_bag_of_words_reader(tmp_path):
+    """docword/vocab files (UCI format, 1-based, unsorted, with a duplicate line) -> CSR."""
+    (tmp_path / "docword.toy.txt").write_text("4\n5\n7\n3 2 4\n1 1 2\n1 5 1\n3 1 1\n4 3 9\n1 1 3\n3 5 2\n")
+    (tmp_path / "vocab.toy.txt").write_text("alpha\nbeta\ngamma\ndelta\nepsilon\n")
+    d = Document.from_uci(tmp_path / "docword.toy.txt", tmp_path / "vocab.toy.txt")
+    rp, ci, ct = d._host_csr
+    assert d.M == 4 and d.V == 5
+    np.testing.assert_array_equal(rp, [0, 2, 2, 5, 6])  # document 2 is empty
+    np.testing.assert_array_equal(ci, [0, 4, 0, 1, 4, 2])
+    np.testing.assert_array_equal(ct, [5, 1, 1, 4, 2, 9])  # the duplicated (1,1) line is summed
+    assert d.idx_to_vocab[2] == "gamma" and d.vocab_to_idx["epsilon"] == 4
+    X = d.doc_vocab_count_array
+    assert X[0, 0] == 5 and X[3, 2] == 9 and X.sum() == 22
+    (tmp_path / "bad.txt").write_text("1\n2\n2\n1 1 1\n")
+    with pytest.raises(ValueError):
+        Document.from_uci(tmp_path / "bad.txt")

@@ -38,6 +38,8 @@ SIGNATURES = {
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                        _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_estep_fixed_point_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
+                                                   _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_sstats_atomic_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
@@ -67,7 +69,8 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
     "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2,
-    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1,
+    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
+    "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1,
     "ttlda_mstep_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
@@ -200,6 +203,15 @@ def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_i
           max_iter, tol, iters, partial, ws):
     D, ld = gamma_out.shape
     _call("ttlda_estep_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
+          _p(alpha_vec, f64), float(alpha_sum), _p(eT_in, f64), _p(eB, f64), _p(gamma_in, f64), _p(gamma_out, f64),
+          _p(eT_out, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
+          ws.numel() * ws.element_size(), _stream())
+
+
+def estep_fixed_point(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out,
+                      max_iter, tol, iters, partial, ws):
+    D, ld = gamma_out.shape
+    _call("ttlda_estep_fixed_point_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
           _p(alpha_vec, f64), float(alpha_sum), _p(eT_in, f64), _p(eB, f64), _p(gamma_in, f64), _p(gamma_out, f64),
           _p(eT_out, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
           ws.numel() * ws.element_size(), _stream())

@@ -16,7 +16,8 @@ from . import _native as nv
 class DeviceCorpus:
     """rowptr int64[D+1], colidx int32[nnz] (ascending per row), counts int32[nnz] and the CSC mirror, on one device."""
 
-    L2_WINDOW_BYTES = 48 << 20   # exp(E[log theta]) rows one document block may occupy (126 MB L2 on B200)
+    L2_WINDOW_BYTES = 96 << 20   # exp(E[log theta]) rows one document block may occupy (126 MB L2 on B200;
+                                 # measured optimum at cfg3: 8-12 blocks of 66-100 MB, DESIGN.md §5)
     MAX_BLOCK_BYTES = 2 << 30    # cap on the per-block statistics buffer nblocks * V * ld * 8
 
     def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = False):

@@ -105,6 +105,38 @@ class Document:
         return cls.from_csr(np.cumsum(rowptr), cols, vals.astype(np.int32), X.shape[1], num_doc_population,
                             idx_to_vocab)
 
+    @classmethod
+    def from_uci(cls, docword_path, vocab_path=None, num_doc_population=None):
+        """UCI "Bag of Words" format (docword.*.txt[.gz]: D, W, NNZ header lines, then `docID wordID count`,
+        1-based) straight to CSR — the ingestion path for real corpora such as NYTimes; the
+        reference can only ingest raw text through its O(V*M) Python loops.  vocab.*.txt gives idx_to_vocab."""
+        import pandas as pd
+
+        with (__import__("gzip").open(docword_path, "rt") if str(docword_path).endswith(".gz")
+              else open(docword_path)) as f:
+            D, W, NNZ = (int(f.readline()) for _ in range(3))
+            t = pd.read_csv(f, sep=r"\s+", header=None, names=["d", "w", "c"], dtype=np.int64, engine="c")
+        if len(t) != NNZ:
+            raise ValueError(f"{docword_path}: header says {NNZ} entries, file has {len(t)}")
+        d, w, c = t["d"].to_numpy() - 1, t["w"].to_numpy() - 1, t["c"].to_numpy()
+        if len(t) and (d.min() < 0 or d.max() >= D or w.min() < 0 or w.max() >= W or c.min() < 1):
+            raise ValueError(f"{docword_path}: index or count out of range")
+        key = d * W + w
+        order = np.argsort(key, kind="stable")
+        key, c = key[order], c[order]
+        uk, start = np.unique(key, return_index=True)  # duplicate (doc, word) lines are summed
+        cs = np.add.reduceat(c, start) if len(c) else c
+        rowptr = np.zeros(D + 1, dtype=np.int64)
+        np.add.at(rowptr, uk // W + 1, 1)
+        vocab = None
+        if vocab_path is not None:
+            with open(vocab_path) as f:
+                vocab = {i: line.rstrip("\n") for i, line in enumerate(f)}
+            if len(vocab) != W:
+                raise ValueError(f"{vocab_path}: {len(vocab)} words, docword header says {W}")
+        return cls.from_csr(np.cumsum(rowptr), (uk % W).astype(np.int32), cs.astype(np.int32), W, num_doc_population,
+                            vocab)
+
     # -- device side ---------------------------------------------------------------------------------------------------------
     def device_corpus(self, device):
         """The CSR/CSC doc-term matrix on `device` (built once per device)."""

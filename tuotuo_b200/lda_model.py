@@ -53,7 +53,7 @@ class LDASmoothed:
     """Smoothed LDA, batch variational inference (drop-in for tuotuo.lda_model.LDASmoothed)."""
 
     def __init__(self, num_topics: int, exchangeable_prior: bool = True, verbose: bool = True, *,
-                 device=None, sstats_mode: str = "csc") -> None:
+                 device=None, sstats_mode: str = "csc", inner_fixed_point: bool = False) -> None:
         self.K = num_topics
         np.random.seed(SEED)  # lda_model.py:71 (global side effect, kept)
         if exchangeable_prior:
@@ -72,6 +72,10 @@ class LDASmoothed:
         if sstats_mode not in ("csc", "atomic"):
             raise ValueError("sstats_mode must be 'csc' (two-pass, reproducible) or 'atomic' (one pass, red.f64)")
         self._sstats_mode = sstats_mode
+        # opt-in: refresh exp(E[log theta_d]) inside the per-document loop (true fixed point) instead of
+        # reproducing the reference's frozen-theta loop; NOT parity with the reference by construction
+        self._inner_fixed_point = bool(inner_fixed_point)
+        self.inner_iterations = 0  # inner passes of the last E-step, summed over documents
         self._fused_refresh = os.environ.get("TTLDA_FUSED_REFRESH", "0") == "1"
         self._device = device
         self._st = None
@@ -233,7 +237,11 @@ class LDASmoothed:
         token term of the CURRENT state (part[0][0]), which completes its perplexity."""
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
-        if self._fused_refresh:
+        if self._inner_fixed_point:
+            nv.estep_fixed_point(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(),
+                                 st.eT[cur], st.eB, st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step,
+                                 e_threshold, st.iters, st.part[0], st.ws)
+        elif self._fused_refresh:
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
                      st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws)
         else:
@@ -247,11 +255,12 @@ class LDASmoothed:
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
         adopt the E-step's gamma / exp(E[log theta])."""
         st, c = self._st, self._st.corpus
+        # the statistics use the theta the E-step read — or, in fixed-point mode, the refreshed one it produced
+        eT = st.eT[st.cur ^ 1] if self._inner_fixed_point else st.eT[st.cur]
         if self._sstats_mode == "atomic":
-            nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, st.eT[st.cur], st.eB, st.sstats)
+            nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
         else:
-            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[st.cur], st.eB, st.sstats,
-                          st.ws_s)
+            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink (SURVEY §8e)
@@ -339,7 +348,7 @@ class LDASmoothed:
             # E-step `it` also completes the perplexity of state `it` (initial perplexity for it == 0, :373-378;
             # perplexity after em_step it-1 otherwise, :403-409)
             self._estep_speculative(e_num_step)
-            _, capped = self._collect(tok_row=0)
+            self.inner_iterations, capped = self._collect(tok_row=0)
             perplexity_orig, perplexity = perplexity, self._perplexity_from_terms(sampling)
             perplexities.append(np.float64(perplexity))
             if it == 0 and verbose:
