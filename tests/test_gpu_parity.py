@@ -425,7 +425,10 @@ def test_inner_fixed_point_mode_vs_oracle(K, V, D, L):
     assert o.inner_iters > 4 * 3 * D  # the loop really iterates (the frozen-theta reference makes 2 passes)
     assert relerr(m._last_elbo, o.last_elbo) < 1e-10 and relerr(pg, po) < TOL_PERP
     assert relerr(m._gamma_, o.gamma) < 1e-8 and relerr(m._lambda_, o.lam) < 1e-8
-    # and it is a different (better-converged) answer than the reference-parity mode
+    # and it is a different (better-converged) answer than the reference-parity mode: higher ELBO after 3 EM steps
+    # (ELBOs, not perplexities: exp() overflows to inf on the tiny K*V >> tokens corpora used here)
+    fp = LDASmoothed(K, verbose=False, inner_fixed_point=True)
+    fp.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False)
     ref = LDASmoothed(K, verbose=False)
-    pr = ref.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False, return_perplexities=True)
-    assert pg[3] < pr[3]
+    ref.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False)
+    assert fp._last_elbo > ref._last_elbo and fp.inner_iterations > ref.inner_iterations == 2 * D
