@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld, K = P.K;
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
+    const uint64_t pol = l2_evict_first_policy();
 
     double lga = 0., lg_asum = 0.;
     if (REFRESH) {
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
         // (word, count) pairs: 32 per coalesced load, fetched ONE batch ahead so that their latency is hidden
         int nx_w = 0, nx_c = 0;
         if (b + lane < e) {
-            nx_w = ld_stream_s32(P.colidx + b + lane);
-            nx_c = ld_stream_s32(P.counts + b + lane);
+            nx_w = ld_stream_s32(P.colidx + b + lane, pol);
+            nx_c = ld_stream_s32(P.counts + b + lane, pol);
         }
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
             nx_w = 0;
             nx_c = 0;
             if (n0 + 32 + lane < e) {
-                nx_w = ld_stream_s32(P.colidx + n0 + 32 + lane);
-                nx_c = ld_stream_s32(P.counts + n0 + 32 + lane);
+                nx_w = ld_stream_s32(P.colidx + n0 + 32 + lane, pol);
+                nx_c = ld_stream_s32(P.counts + n0 + 32 + lane, pol);
             }
             double my_p = 1.;
             walk_rows<G, E, PREFETCH>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
@@ -126,9 +127,9 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                     double a = 0.;
 #pragma unroll
                     for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
-                    gn[m] = P.alpha_vec[k] + P.eT_in[d * P.ld + k] * a;  // lda_model.py:248
+                    gn[m] = P.alpha_vec[k] + ld_stream_f64(P.eT_in + d * P.ld + k, pol) * a;  // lda_model.py:248
                     s += gn[m];
-                    if (P.iters) l1 += fabs(gn[m] - P.gamma_in[d * P.ld + k]);
+                    if (P.iters) l1 += fabs(gn[m] - ld_stream_f64(P.gamma_in + d * P.ld + k, pol));
                 }
             }
             __syncwarp();
@@ -153,8 +154,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                         psi_lgamma_as103(gn[m], ps, lg);
                         const double el = ps - pt;
                         th += (P.alpha_vec[k] - gn[m]) * el + lg;
-                        P.gamma_out[d * P.ld + k] = gn[m];
-                        P.eT_out[d * P.ld + k] = exp(el);
+                        st_stream_f64(P.gamma_out + d * P.ld + k, gn[m], pol);
+                        st_stream_f64(P.eT_out + d * P.ld + k, exp(el), pol);
                     }
                 }
                 if (lane < ld - K) {  // padding columns
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
 #pragma unroll
                 for (int m = 0; m < MMAX; ++m) {
                     const int k = lane + 32 * m;
-                    if (k < K) P.gamma_out[d * P.ld + k] = gn[m];
+                    if (k < K) st_stream_f64(P.gamma_out + d * P.ld + k, gn[m], pol);
                 }
                 if (lane < ld - K) P.gamma_out[d * P.ld + K + lane] = 0.;
             }

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(kFpThreads) doc_fixed_point_kernel(const Fixed
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld, K = P.K;
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
+    const uint64_t pol = l2_evict_first_policy();
 
     double lga = 0.;
     for (int k = lane; k < K; k += 32) lga += lgamma(P.alpha_vec[k]);
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(kFpThreads) doc_fixed_point_kernel(const Fixed
                 const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
                 int my_w = 0, my_c = 0;
                 if (lane < cnt) {
-                    my_w = ld_stream_s32(P.colidx + n0 + lane);
-                    my_c = ld_stream_s32(P.counts + n0 + lane);
+                    my_w = ld_stream_s32(P.colidx + n0 + lane, pol);
+                    my_c = ld_stream_s32(P.counts + n0 + lane, pol);
                 }
                 double my_p = 1.;
                 walk_rows<G, E, PF>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int sb, const KSlice<G, E>& row) {

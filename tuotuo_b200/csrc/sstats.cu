@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld;
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
+    const uint64_t pol = l2_evict_first_policy();
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
         const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
             // (document, count) pairs: 32 per coalesced load, fetched ONE batch ahead
             int nx_d = 0, nx_c = 0;
             if (pos + lane < se) {
-                nx_d = ld_stream_s32(P.docidx + pos + lane);
-                nx_c = ld_stream_s32(P.ccounts + pos + lane);
+                nx_d = ld_stream_s32(P.docidx + pos + lane, pol);
+                nx_c = ld_stream_s32(P.ccounts + pos + lane, pol);
             }
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
@@ -106,8 +107,8 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
                 nx_d = 0;
                 nx_c = 0;
                 if (n0 + 32 + lane < se) {
-                    nx_d = ld_stream_s32(P.docidx + n0 + 32 + lane);
-                    nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane);
+                    nx_d = ld_stream_s32(P.docidx + n0 + 32 + lane, pol);
+                    nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane, pol);
                 }
                 walk_rows<G, E, PREFETCH>(P.eT, P.ld, my_d, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
                     const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
                     double a = 0.;
 #pragma unroll
                     for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
-                    dst[k] = a;
+                    st_stream_f64(dst + k, a, pol);
                 }
             }
             __syncwarp();

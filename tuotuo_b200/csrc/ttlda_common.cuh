@@ -140,11 +140,32 @@ __device__ __forceinline__ double psi_exact(double x)
 // read-only path; streaming data (CSR arrays) goes through L1::no_allocate.
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
-__device__ __forceinline__ int ld_stream_s32(const int32_t* p)
+// L2 eviction policy for data that is touched once per pass (CSR/CSC index streams, theta/gamma tables, statistics
+// output): evict-first, so that the streams do not push the re-used K-vector tables out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_evict_first_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+
+__device__ __forceinline__ int ld_stream_s32(const int32_t* p, uint64_t pol)
 {
     int v;
-    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
+}
+
+__device__ __forceinline__ double ld_stream_f64(const double* p, uint64_t pol)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ void st_stream_f64(double* p, double v, uint64_t pol)
+{
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
 }
 
 // final fixed-order reduction of per-CTA records: out[j] = sum_b rec[b][j]
