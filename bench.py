@@ -40,9 +40,9 @@ UNIT = "doc-tokens/s"
 def algorithmic_bytes(nnz, D, K, V):
     """Gather-model bytes.  Per launch of each kernel and per EM iteration."""
     kb = 8 * K
-    est = nnz * (kb + 8) + D * kb * 4 + (D + 1) * 8      # gather eB row + (colidx,count); eT in x2, gamma in/out
+    est = nnz * (kb + 8 + 12) + D * kb * 4 + (D + 1) * 8  # gather eB row + (colidx,count) + (csr2csc, ratio out); eT in x2, gamma in/out
     ref = D * kb * 2                                       # theta refresh pass: gamma in, eT out
-    sst = nnz * (kb + 8) + V * kb * 2 + (V + 1) * 8      # gather eT row + (docidx,count); eB in, S out
+    sst = nnz * (kb + 12) + V * kb + (V + 1) * 8         # gather eT row + (docidx, ratio in); S out
     mst = V * kb * 6                                       # S, eB in; lambda out; lambda in; eB out (+colsum pass)
     # the ELBO token term is a by-product of the E-step (same dot product): no third gather => 16K bytes per nonzero
     return {"ttlda_estep_f64": est, "ttlda_sstats_csc_f64": sst, "ttlda_mstep_f64": mst,

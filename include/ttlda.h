@@ -78,11 +78,13 @@ int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64
  * matrix of tuotuo/document.py:36 is addressable both ways; the CSC copy gives the M-step the same access.
  * With nblocks > 1 the mirror is DOCUMENT-BLOCKED: documents are cut into nblocks blocks of block_docs documents
  * and "virtual word" b*V + w lists the postings of word w inside block b (colptr has nblocks*V + 1 entries), so
- * that the statistics pass gathers exp(E[log theta]) rows from one L2-sized window of the D x K table at a time. */
+ * that the statistics pass gathers exp(E[log theta]) rows from one L2-sized window of the D x K table at a time.
+ * csr2csc (uint32[nnz], may be NULL): position in the mirror of every CSR position — lets the E-step leave the
+ * per-nonzero ratio c/N for the statistics pass in mirror order (ttlda_estep_f64 `ratio_csc`). */
 int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int64_t nblocks);
 int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
                      int64_t D, int64_t V, int64_t nnz, int64_t nblocks, int64_t block_docs,
-                     int64_t* colptr, int32_t* docidx, int32_t* ccounts,
+                     int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
@@ -116,6 +118,9 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
  *   gamma_in: the previous gamma [D][ld]; read only for the loop statistics (may be NULL iff iters_out is NULL,
  *   may alias gamma_out).  gamma_out / exp_elogtheta_out are written; exp_elogtheta_out must not alias the input
  *   (ping-pong), which lets a caller run the pass speculatively and discard it.
+ *   csr2csc / ratio_csc (both or neither): if given, ratio_csc[csr2csc[p]] = c_p / N_p is stored for every nonzero p
+ *   (one double per nonzero — not phi): the statistics pass then needs no dot product, reduction or division
+ *   (ttlda_sstats_csc_f64 `ratio_csc`).
  *   partial_out double[TTLDA_NPART]: [0] token term at the incoming state, [1] theta-prior term at the outgoing
  *   state, [2] sum of counts.
  */
@@ -124,6 +129,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     const double* alpha_vec, double alpha_sum,
                     const double* exp_elogtheta_in, const double* exp_elogbeta,
                     const double* gamma_in, double* gamma_out, double* exp_elogtheta_out,
+                    const uint32_t* csr2csc, double* ratio_csc,
                     int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
                     void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -150,11 +156,15 @@ int ttlda_estep_fixed_point_f64(const int64_t* rowptr, const int32_t* colidx, co
  * `*= exp(Elogbeta)` of :264 is applied by ttlda_mstep_f64, after the cross-GPU sum — it is linear).
  * colptr/docidx/ccounts: the (possibly document-blocked, nblocks >= 1) mirror built by ttlda_csr_to_csc; per-block
  * partial statistics live in the workspace and are folded in block order; sstats [V][ld] is the total.
+ * ratio_csc (double[nnz] in mirror order, may be NULL): the c/N ratios left by ttlda_estep_f64 for the SAME
+ * exp_elogtheta / exp_elogbeta; when given the pass is a pure gather-accumulate S[w,:] += ratio * eT[d,:]
+ * (exp_elogbeta is then unused and may be NULL), otherwise the normaliser is recomputed from the two tables.
  */
 int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks);
 int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts,
                          int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks,
-                         const double* exp_elogtheta, const double* exp_elogbeta, double* sstats,
+                         const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
+                         double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* One-pass alternative to ttlda_sstats_csc_f64 (the north-star's literal formulation): document-major scatter of

@@ -38,13 +38,17 @@ def csr_to_csc_workspace_bytes(nnz, D, V, nblocks=1):
     return 64
 
 
-def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, docidx, ccounts, ws):
+def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, docidx, ccounts, ws, csr2csc=None):
     rp, ci, ct = _np(rowptr), _np(colidx)[:nnz], _np(counts)[:nnz]
     docs = np.repeat(np.arange(D), np.diff(rp))
     keys = (docs // block_docs) * V + ci
     order = np.argsort(keys, kind="stable")
     _np(docidx)[:nnz] = docs[order]
     _np(ccounts)[:nnz] = ct[order]
+    if csr2csc is not None:
+        inv = np.empty(nnz, dtype=np.int64)
+        inv[order] = np.arange(nnz)
+        _np(csr2csc)[:nnz] = inv.astype(np.int32)
     cp = np.zeros(nblocks * V + 1, dtype=np.int64)
     np.add.at(cp, keys + 1, 1)
     _np(colptr)[:] = np.cumsum(cp)
@@ -100,11 +104,13 @@ def _coo(rowptr, colidx, counts):
 
 
 def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out, max_iter, tol,
-          iters, partial, ws):
+          iters, partial, ws, csr2csc=None, ratio_csc=None):
     d, w, c = _coo(rowptr, colidx, counts)
     t, b, a = _np(eT_in)[:, :K], _np(eB)[:, :K], _np(alpha_vec)
     dot = np.einsum("ik,ik->i", t[d], b[w])
     r = c / (dot + 1e-100)
+    if ratio_csc is not None:
+        _np(ratio_csc)[_np(csr2csc)[:len(r)].astype(np.int64)] = r
     acc = np.zeros_like(t)
     np.add.at(acc, d, r[:, None] * b[w])
     g_new = a + t * acc
@@ -135,14 +141,17 @@ def elbo_tokens(rowptr, colidx, counts, K, eT, eB, partial, ws):
     p[2] = float(c.sum())
 
 
-def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws):
+def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, ratio_csc=None):
     cp = _np(colptr)
     vw = np.repeat(np.arange(len(cp) - 1), np.diff(cp))
     w = vw % V
     d = _np(docidx)[:nnz].astype(np.int64)
     c = _np(ccounts)[:nnz].astype(np.float64)
     t, b = _np(eT)[:, :K], _np(eB)[:, :K]
-    r = c / (np.einsum("ik,ik->i", t[d], b[w]) + 1e-100)
+    if ratio_csc is not None:
+        r = _np(ratio_csc)[:nnz]
+    else:
+        r = c / (np.einsum("ik,ik->i", t[d], b[w]) + 1e-100)
     S = _np(sstats)
     S[:] = 0.0
     np.add.at(S[:, :K], w, r[:, None] * t[d])

@@ -52,8 +52,8 @@ def test_argument_validation_without_gpu(lib_path):
     from tuotuo_b200 import _native as nv
 
     lib = nv.load()
-    rc = lib.ttlda_estep_f64(None, None, None, 1, 5, 10, 8, None, 1.0, None, None, None, None, None, 1, 1e-5,
-                             None, None, None, 0, None)
+    rc = lib.ttlda_estep_f64(None, None, None, 1, 5, 10, 8, None, 1.0, None, None, None, None, None, None, None, 1,
+                             1e-5, None, None, None, 0, None)
     assert rc == -1 and b"NULL" in lib.ttlda_last_error()
     rc = lib.ttlda_dirichlet_expectation_f64(None, 1, 1, 4, None, None, None)
     assert rc == -1

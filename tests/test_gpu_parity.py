@@ -164,7 +164,7 @@ def test_bow_to_csr_and_csc_bit_exact(golden_dir, nv, dev):
 
 
 # ------------------------------------------------------------------------------------------------------------------
-def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1):
+def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1, handoff=False):
     """theta/beta refresh -> estep -> sstats -> mstep -> tokens, all through the C ABI; returns host results."""
     from tuotuo_b200.corpus import DeviceCorpus
 
@@ -192,11 +192,13 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1)
     nv.beta_refresh(lam, K, 1.0, eB, None, colsum, part[1], ws_m)
     nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, eT0, eB, part[2], ws)
     elbo0 = float(part[0, 0] + part[1, 0] + part[2, 0])
-    nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, 100, 1e-5, iters, part[3], ws)
+    ratio = torch.full((max(c.nnz, 1),), float("nan"), dtype=torch.float64, device=dev) if handoff else None
+    nv.estep(c.rowptr, c.colidx, c.counts, K, V, av, asum, eT0, eB, gamma, gamma, eT1, 100, 1e-5, iters, part[3], ws,
+             c.csr2csc if handoff else None, ratio)
     if mode == "atomic":
         nv.sstats_atomic(c.rowptr, c.colidx, c.counts, K, V, eT0, eB, S)
     else:
-        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, c.nblocks, eT0, eB, S, ws_s)
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, c.nnz, c.nblocks, eT0, eB, S, ws_s, ratio)
     upd = torch.empty((K, V), dtype=torch.float64, device=dev)
     nv.transpose_unpad(S * eB, K, upd)
     elog_b = torch.zeros_like(lam)
@@ -213,11 +215,12 @@ def _single_step(nv, dev, X: CSRCorpus, K, gamma0, lam0, alpha, mode, nblocks=1)
                     gamma[:, K:].abs().sum() + eT1[:, K:].abs().sum() + lam_new[:, K:].abs().sum() + eB[:, K:].abs().sum()))
 
 
-@pytest.mark.parametrize("mode,nblocks", [("csc", 1), ("csc", 3), ("csc", 200), ("atomic", 1)])
-def test_single_em_step_vs_reference(golden_dir, nv, dev, mode, nblocks):
+@pytest.mark.parametrize("mode,nblocks,handoff", [("csc", 1, False), ("csc", 3, False), ("csc", 200, False),
+                                                  ("csc", 1, True), ("csc", 5, True), ("atomic", 1, False)])
+def test_single_em_step_vs_reference(golden_dir, nv, dev, mode, nblocks, handoff):
     g = _load(golden_dir, "estep_small.npz")
     X = CSRCorpus(g["rowptr"], g["colidx"], g["counts"], int(g["V"]))
-    r = _single_step(nv, dev, X, int(g["K"]), g["gamma0"], g["lam0"], 1, mode, nblocks)
+    r = _single_step(nv, dev, X, int(g["K"]), g["gamma0"], g["lam0"], 1, mode, nblocks, handoff)
     assert relerr(r["elbo0"], g["elbo0"]) < 1e-12
     assert relerr(r["gamma"], g["gamma1"]) < TOL_STATE
     assert relerr(r["sstats"], g["sstats1"]) < TOL_STATE
@@ -432,3 +435,21 @@ def test_inner_fixed_point_mode_vs_oracle(K, V, D, L):
     ref = LDASmoothed(K, verbose=False)
     ref.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False)
     assert fp._last_elbo > ref._last_elbo and fp.inner_iterations > ref.inner_iterations == 2 * D
+
+
+def test_ratio_handoff_and_recompute_agree(monkeypatch):
+    """The statistics pass fed with the E-step's c/N ratios equals the pass that recomputes the normaliser."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(55, 500, 700, 20, 60, ragged=True)
+    res = {}
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TTLDA_RATIO_HANDOFF", flag)
+        m = LDASmoothed(64, verbose=False)
+        p = m.fit(Document.from_csr(rp, ci, ct, 700), em_num_step=3, return_perplexities=True)
+        assert (m._st.ratio is not None) == (flag == "1")
+        res[flag] = (p, m._lambda_.copy(), m._gamma_.copy())
+    assert relerr(res["1"][0], res["0"][0]) < 1e-13
+    assert relerr(res["1"][1], res["0"][1]) < 1e-12 and relerr(res["1"][2], res["0"][2]) < 1e-12

@@ -32,18 +32,18 @@ SIGNATURES = {
     "ttlda_bow_to_csr_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "ttlda_bow_to_csr": (ctypes.c_int, [_ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_csr_to_csc_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
-    "ttlda_csr_to_csc": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
-                                        _ptr]),
+    "ttlda_csr_to_csc": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                        _i64, _ptr]),
     "ttlda_reduce_workspace_bytes": (_i64, []),
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
-                                       _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+                                       _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_fixed_point_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
                                                    _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_sstats_atomic_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
-                                            _i64, _ptr]),
+                                            _ptr, _i64, _ptr]),
     "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
@@ -188,9 +188,10 @@ def csr_to_csc_workspace_bytes(nnz, D, V, nblocks=1) -> int:
     return r
 
 
-def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, docidx, ccounts, ws):
+def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, docidx, ccounts, ws, csr2csc=None):
     _call("ttlda_csr_to_csc", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), int(D), int(V), int(nnz),
-          int(nblocks), int(block_docs), _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), _p(ws), ws.numel() * ws.element_size(), _stream())
+          int(nblocks), int(block_docs), _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), _p(csr2csc, torch.int32),
+          _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
 def theta_refresh(gamma, K, alpha_vec, alpha_sum, eT, partial, ws):
@@ -200,11 +201,11 @@ def theta_refresh(gamma, K, alpha_vec, alpha_sum, eT, partial, ws):
 
 
 def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out,
-          max_iter, tol, iters, partial, ws):
+          max_iter, tol, iters, partial, ws, csr2csc=None, ratio_csc=None):
     D, ld = gamma_out.shape
     _call("ttlda_estep_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), int(V), ld,
           _p(alpha_vec, f64), float(alpha_sum), _p(eT_in, f64), _p(eB, f64), _p(gamma_in, f64), _p(gamma_out, f64),
-          _p(eT_out, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
+          _p(eT_out, f64), _p(csr2csc, torch.int32), _p(ratio_csc, f64), int(max_iter), float(tol), _p(iters, i64), _p(partial, f64), _p(ws),
           ws.numel() * ws.element_size(), _stream())
 
 
@@ -221,12 +222,12 @@ def sstats_workspace_bytes(nnz, V, ld, nblocks=1) -> int:
     return int(load().ttlda_sstats_workspace_bytes(int(nnz), int(V), int(ld), int(nblocks)))
 
 
-def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws):
+def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, ratio_csc=None):
     global kernel_count
-    ld = eB.shape[1]
+    ld = eT.shape[1]
     kernel_count += 1 if nblocks > 1 else 0  # + sstats_fold_kernel
     _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), int(V), int(K), ld, int(nnz),
-          int(nblocks), _p(eT, f64), _p(eB, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+          int(nblocks), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
 def sstats_atomic(rowptr, colidx, counts, K, V, eT, eB, sstats):

@@ -28,7 +28,7 @@ class DeviceCorpus:
         self.V = int(V)
         self.nnz = int(colidx.numel())
         self.tokens = int(counts.sum(dtype=torch.int64).item()) if self.nnz else 0
-        self.colptr = self.docidx = self.ccounts = None
+        self.colptr = self.docidx = self.ccounts = self.csr2csc = None
         self.nblocks, self.block_docs = 0, 0
         if build_csc:
             self.build_csc()
@@ -86,8 +86,9 @@ class DeviceCorpus:
         if self.docidx is None:
             self.docidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
             self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+            self.csr2csc = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)  # uint32 bit patterns
         nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
-                      self.colptr, self.docidx, self.ccounts, ws)
+                      self.colptr, self.docidx, self.ccounts, ws, self.csr2csc)
         self.nblocks, self.block_docs = nblocks, block_docs
         del ws
 
@@ -113,7 +114,7 @@ class DeviceCorpus:
     def nbytes(self) -> int:
         n = self.rowptr.numel() * 8 + self.nnz * 8
         if self.colptr is not None:
-            n += self.colptr.numel() * 8 + self.nnz * 8
+            n += self.colptr.numel() * 8 + self.nnz * 12
         return n
 
 

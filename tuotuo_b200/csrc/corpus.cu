@@ -75,7 +75,7 @@ __global__ void csc_keys_kernel(const int64_t* __restrict__ rowptr, const int32_
 __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ spos,
                                   const uint32_t* __restrict__ docs, const int32_t* __restrict__ counts, int64_t VV,
                                   int64_t nnz, int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
-                                  int32_t* __restrict__ ccounts)
+                                  int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t wcur = (i < nnz) ? (int64_t)skeys[i] : VV;
@@ -85,6 +85,7 @@ __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint
             const int64_t p = spos[i];
             docidx[i] = (int32_t)docs[p];
             ccounts[i] = counts[p];
+            if (csr2csc) csr2csc[p] = (uint32_t)i;  // where CSR position p lives in the mirror
         }
     }
 }
@@ -210,7 +211,7 @@ int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int6
 
 int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
                      int64_t nnz, int64_t nblocks, int64_t block_docs, int64_t* colptr, int32_t* docidx,
-                     int32_t* ccounts, void* workspace, int64_t workspace_bytes, void* stream)
+                     int32_t* ccounts, uint32_t* csr2csc, void* workspace, int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(rowptr && colptr && workspace, "NULL pointer");
     TTLDA_REQUIRE(nnz == 0 || (colidx && counts && docidx && ccounts), "NULL pointer");
@@ -235,7 +236,7 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
         if (e != cudaSuccess) return cuda_fail(e, "radix sort (csc)");
     }
     csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, w.docs, counts, VV, nnz, colptr, docidx,
-                                                       ccounts);
+                                                       ccounts, csr2csc);
     TTLDA_LAUNCH_CHECK("csc_gather");
     return TTLDA_OK;
 }

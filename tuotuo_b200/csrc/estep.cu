@@ -34,6 +34,8 @@ struct EStepParams {
     const double* gamma_in;  // previous gamma (only read for the loop statistics), may be NULL
     double* gamma_out;
     double* eT_out;
+    const uint32_t* csr2csc;  // mirror position of every CSR position, or NULL
+    double* ratio_csc;        // c/N per nonzero in mirror order (for the statistics pass), or NULL
     int64_t max_iter;
     double tol;
     unsigned long long* iters;  // [2] device counters (passes, capped docs) or NULL
@@ -80,19 +82,22 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
         acc.zero();
 
         // (word, count) pairs: 32 per coalesced load, fetched ONE batch ahead so that their latency is hidden
-        int nx_w = 0, nx_c = 0;
+        int nx_w = 0, nx_c = 0, nx_pos = 0;
         if (b + lane < e) {
             nx_w = ld_stream_s32(P.colidx + b + lane, pol);
             nx_c = ld_stream_s32(P.counts + b + lane, pol);
+            if (ESTEP && P.ratio_csc) nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + b + lane, pol);
         }
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
-            const int my_w = nx_w, my_c = nx_c;
+            const int my_w = nx_w, my_c = nx_c, my_pos = nx_pos;
             nx_w = 0;
             nx_c = 0;
             if (n0 + 32 + lane < e) {
                 nx_w = ld_stream_s32(P.colidx + n0 + 32 + lane, pol);
                 nx_c = ld_stream_s32(P.counts + n0 + 32 + lane, pol);
+                if (ESTEP && P.ratio_csc)
+                    nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + n0 + 32 + lane, pol);
             }
             double my_p = 1.;
             walk_rows<G, E, PREFETCH>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
@@ -110,6 +115,9 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
             if (lane < cnt) {  // one log per nonzero
                 tok_acc += (double)my_c * log(my_p);
                 cnt_acc += (double)my_c;
+                // leave c/N for the statistics pass, in mirror (word-major) order: one scattered 8-byte store
+                if (ESTEP && P.ratio_csc)
+                    st_stream_f64(P.ratio_csc + (uint32_t)my_pos, (double)my_c / (my_p + 1e-100), pol);
             }
         }
 
@@ -230,7 +238,8 @@ extern "C" {
 int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t K,
                     int64_t V, int64_t ld, const double* alpha_vec, double alpha_sum,
                     const double* exp_elogtheta_in, const double* exp_elogbeta, const double* gamma_in,
-                    double* gamma_out, double* exp_elogtheta_out, int64_t max_iter, double tol,
+                    double* gamma_out, double* exp_elogtheta_out, const uint32_t* csr2csc, double* ratio_csc,
+                    int64_t max_iter, double tol,
                     int64_t* iters_out, double* partial_out, void* workspace, int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(rowptr && alpha_vec && exp_elogtheta_in && exp_elogbeta && gamma_out && partial_out && workspace,
@@ -240,6 +249,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
     TTLDA_REQUIRE(exp_elogtheta_in != exp_elogtheta_out, "exp_elogtheta_out must not alias the input");
     TTLDA_REQUIRE(max_iter >= 0, "max_iter must be >= 0");
     TTLDA_REQUIRE(!iters_out || gamma_in, "iters_out needs gamma_in (the previous gamma)");
+    TTLDA_REQUIRE((csr2csc == nullptr) == (ratio_csc == nullptr), "csr2csc and ratio_csc go together");
     if (workspace_bytes < reduce_ws_bytes()) {
         set_error("estep: workspace %lld < %lld", (long long)workspace_bytes, (long long)reduce_ws_bytes());
         return TTLDA_EWORKSPACE;
@@ -250,7 +260,7 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
         if (e != cudaSuccess) return cuda_fail(e, "memset iters");
     }
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta_in, exp_elogbeta,
-                  gamma_in, gamma_out, exp_elogtheta_out, max_iter, tol,
+                  gamma_in, gamma_out, exp_elogtheta_out, csr2csc, ratio_csc, max_iter, tol,
                   (unsigned long long*)iters_out, (double*)workspace};
     int rc = exp_elogtheta_out ? launch_doc_pass<1>(P, s) : launch_doc_pass<2>(P, s);
     if (rc != TTLDA_OK) return rc;
@@ -271,7 +281,7 @@ int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const in
     }
     cudaStream_t s = (cudaStream_t)stream;
     EStepParams P{rowptr, colidx, counts, D, (int)K, ld, nullptr, 0., exp_elogtheta, exp_elogbeta,
-                  nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
+                  nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0., nullptr, (double*)workspace};
     int rc = launch_doc_pass<0>(P, s);
     if (rc != TTLDA_OK) return rc;
     TTLDA_LAUNCH_CHECK("elbo_tokens");

@@ -39,12 +39,15 @@ struct SStatsParams {
     int64_t nchunks;
     const double* eT;
     const double* eB;
+    const double* ratio; // c/N per posting in mirror order (left by the E-step), or NULL => recompute
     double* S;           // [VV][ld] per-(block, word) statistics (== the final [V][ld] table when nblocks == 1)
     double* carry;       // [nchunks][2][ld]  head / tail partials of words cut by a chunk boundary
     int32_t* carry_word; // [nchunks][2]      virtual word id of each carry slot, -1 = unused
 };
 
-template <int G, int E, bool PREFETCH>
+// USE_RATIO: the E-step left c/N per posting (ttlda_estep_f64 ratio_csc): the pass is then a pure gather-accumulate
+// S[w,:] += ratio * eT[d,:] — no beta K-vector in registers, no dot product, shuffle reduction or division.
+template <int G, int E, bool PREFETCH, bool USE_RATIO>
 __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_kernel(const SStatsParams P)
 {
     constexpr int R = 32 / G;
@@ -92,28 +95,37 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_ker
             }
             const int64_t se = (we < ce) ? we : ce;  // segment [pos, se) of virtual word w
             KSlice<G, E> b, acc;
-            b.load(P.eB + (w % P.V) * P.ld, g, last_ok);
+            if (!USE_RATIO) b.load(P.eB + (w % P.V) * P.ld, g, last_ok);
             acc.zero();
 
-            // (document, count) pairs: 32 per coalesced load, fetched ONE batch ahead
+            // (document, count | ratio) pairs: 32 per coalesced load, fetched ONE batch ahead
             int nx_d = 0, nx_c = 0;
+            double nx_r = 0.;
             if (pos + lane < se) {
                 nx_d = ld_stream_s32(P.docidx + pos + lane, pol);
-                nx_c = ld_stream_s32(P.ccounts + pos + lane, pol);
+                if (USE_RATIO) nx_r = ld_stream_f64(P.ratio + pos + lane, pol);
+                else nx_c = ld_stream_s32(P.ccounts + pos + lane, pol);
             }
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
                 const int my_d = nx_d, my_c = nx_c;
+                const double my_r = nx_r;
                 nx_d = 0;
                 nx_c = 0;
+                nx_r = 0.;
                 if (n0 + 32 + lane < se) {
                     nx_d = ld_stream_s32(P.docidx + n0 + 32 + lane, pol);
-                    nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane, pol);
+                    if (USE_RATIO) nx_r = ld_stream_f64(P.ratio + n0 + 32 + lane, pol);
+                    else nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane, pol);
                 }
                 walk_rows<G, E, PREFETCH>(P.eT, P.ld, my_d, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
-                    const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
-                    const double p = group_sum<G>(b.dot(row));
-                    acc.axpy((double)cc / (p + 1e-100), row);  // lda_model.py:242,262
+                    if (USE_RATIO) {
+                        acc.axpy(__shfl_sync(0xffffffffu, my_r, s * R + r), row);  // 0 past the end of the segment
+                    } else {
+                        const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
+                        const double p = group_sum<G>(b.dot(row));
+                        acc.axpy((double)cc / (p + 1e-100), row);  // lda_model.py:242,262
+                    }
                 });
             }
             // group partials -> one K-vector, written with coalesced stores
@@ -184,7 +196,8 @@ static void launch_shape(const SStatsParams& P, int grid, cudaStream_t s)
     constexpr int R = 32 / G;
     constexpr size_t smem = (size_t)(kWordThreads / 32) * R * 2 * G * E * sizeof(double);
     constexpr bool PF = (E <= 8);
-    sstats_csc_kernel<G, E, PF><<<grid, kWordThreads, smem, s>>>(P);
+    if (P.ratio) sstats_csc_kernel<G, E, PF, true><<<grid, kWordThreads, smem, s>>>(P);
+    else sstats_csc_kernel<G, E, PF, false><<<grid, kWordThreads, smem, s>>>(P);
 }
 
 // One-pass alternative (the north-star's literal formulation): document-major scatter with red.global.add.f64.
@@ -229,10 +242,10 @@ int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t
 
 int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t V, int64_t K,
                          int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
-                         const double* exp_elogbeta, double* sstats, void* workspace, int64_t workspace_bytes,
-                         void* stream)
+                         const double* exp_elogbeta, const double* ratio_csc, double* sstats, void* workspace,
+                         int64_t workspace_bytes, void* stream)
 {
-    TTLDA_REQUIRE(colptr && exp_elogtheta && exp_elogbeta && sstats && workspace, "NULL pointer");
+    TTLDA_REQUIRE(colptr && exp_elogtheta && (exp_elogbeta || ratio_csc) && sstats && workspace, "NULL pointer");
     TTLDA_REQUIRE(V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
     TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
     TTLDA_REQUIRE(nblocks >= 1 && nblocks * V < ((int64_t)1 << 31), "bad nblocks");
@@ -259,7 +272,7 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
         }
         return TTLDA_OK;
     }
-    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, nnz, nc, exp_elogtheta, exp_elogbeta, Sb, carry,
+    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, nnz, nc, exp_elogtheta, exp_elogbeta, ratio_csc, Sb, carry,
                    carry_word};
     const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
     GroupShape gs = group_shape_for(ld);

@@ -77,6 +77,7 @@ class LDASmoothed:
         self._inner_fixed_point = bool(inner_fixed_point)
         self.inner_iterations = 0  # inner passes of the last E-step, summed over documents
         self._fused_refresh = os.environ.get("TTLDA_FUSED_REFRESH", "0") == "1"
+        self._ratio_handoff = os.environ.get("TTLDA_RATIO_HANDOFF", "1") == "1"
         self._device = device
         self._st = None
         self._np_cache = {}
@@ -143,11 +144,14 @@ class LDASmoothed:
         st.iters = torch.zeros(2, dtype=torch.int64, device=dev)
         st.ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
         st.ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
-        st.ws_s = None
+        st.ws_s = st.ratio = None
         if self._sstats_mode == "csc":
             corpus.ensure_csc(ld)  # (document-blocked) CSC mirror sized for this K
             st.ws_s = torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld, corpus.nblocks), dtype=torch.uint8,
                                   device=dev)
+            if self._ratio_handoff and not self._inner_fixed_point:
+                # c/N per nonzero, written by the E-step in mirror order, consumed by the statistics pass
+                st.ratio = torch.empty(max(corpus.nnz, 1), dtype=f64, device=dev)
         st.terms = dict(tok=0.0, theta=0.0, beta=0.0, count=0.0)
         self._st = st
         self._np_cache = {}
@@ -243,11 +247,13 @@ class LDASmoothed:
                                  e_threshold, st.iters, st.part[0], st.ws)
         elif self._fused_refresh:
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                     st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws)
+                     st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws,
+                     c.csr2csc if st.ratio is not None else None, st.ratio)
         else:
             # gamma only; the theta refresh (digamma / log-gamma / exp per gamma_dk) runs as its own streaming pass
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                     st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws)
+                     st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
+                     c.csr2csc if st.ratio is not None else None, st.ratio)
             nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
             st.part[0, 1].copy_(st.part[4, 0])
 
@@ -260,7 +266,8 @@ class LDASmoothed:
         if self._sstats_mode == "atomic":
             nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
         else:
-            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s)
+            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
+                          st.ratio)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink
