@@ -48,7 +48,7 @@ struct SStatsParams {
 // USE_RATIO: the E-step left c/N per posting (ttlda_estep_f64 ratio_csc): the pass is then a pure gather-accumulate
 // S[w,:] += ratio * eT[d,:] — no beta K-vector in registers, no dot product, shuffle reduction or division.
 template <int G, int E, bool PREFETCH, bool USE_RATIO>
-__global__ void __launch_bounds__(kWordThreads, (E <= 8 ? 3 : 1)) sstats_csc_kernel(const SStatsParams P)
+__global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 1)) sstats_csc_kernel(const SStatsParams P)
 {
     constexpr int R = 32 / G;
     constexpr int LDP = 2 * G * E;
