@@ -453,3 +453,26 @@ def test_ratio_handoff_and_recompute_agree(monkeypatch):
         res[flag] = (p, m._lambda_.copy(), m._gamma_.copy())
     assert relerr(res["1"][0], res["0"][0]) < 1e-13
     assert relerr(res["1"][1], res["0"][1]) < 1e-12 and relerr(res["1"][2], res["0"][2]) < 1e-12
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_em_step_from_host_equals_resident_iteration(chunks):
+    """Streaming entry point: corpus arrives from pinned host memory in document chunks overlapped with the E-step;
+    results equal the resident-corpus iterations of fit()."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(61, 900, 600, 20, 50, ragged=True)
+    ref = LDASmoothed(40, verbose=False)
+    pr = ref.fit(Document.from_csr(rp, ci, ct, 600), em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    m = LDASmoothed(40, verbose=False)
+    m.fit(Document.from_csr(rp, ci, ct, 600), em_num_step=0, update_hyper_parms=False)
+    h = [torch.as_tensor(a).pin_memory() for a in (rp, ci, ct)]
+    # scribble over the device corpus: the streamed copy must be what the iteration reads
+    m._st.corpus.colidx.zero_()
+    m._st.corpus.counts.zero_()
+    ps = [m.em_step_from_host(*h, chunks=chunks) for _ in range(3)]
+    assert relerr(ps, pr[:3]) < 1e-12  # perplexity of the incoming state of each iteration
+    assert relerr(m._gamma_, ref._gamma_) < 1e-12 and relerr(m._lambda_, ref._lambda_) < 1e-12
+    assert m.inner_iterations == 2 * 900

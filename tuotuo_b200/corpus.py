@@ -74,8 +74,9 @@ class DeviceCorpus:
         nb = max(1, -(-self.D // block_docs))
         return nb, block_docs
 
-    def build_csc(self, nblocks: int = 1, block_docs: int | None = None):
-        """(Re)build the CSC mirror on the device; document-blocked when nblocks > 1 (ttlda_csr_to_csc)."""
+    def build_csc(self, nblocks: int = 1, block_docs: int | None = None, with_map: bool = True):
+        """(Re)build the CSC mirror on the device; document-blocked when nblocks > 1 (ttlda_csr_to_csc).
+        with_map=False skips the csr->csc position map (only the E-step's ratio hand-off needs it)."""
         dev = self.device
         nblocks = max(1, int(nblocks))
         block_docs = int(block_docs) if block_docs else max(1, -(-self.D // nblocks))
@@ -88,7 +89,7 @@ class DeviceCorpus:
             self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
             self.csr2csc = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)  # uint32 bit patterns
         nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
-                      self.colptr, self.docidx, self.ccounts, ws, self.csr2csc)
+                      self.colptr, self.docidx, self.ccounts, ws, self.csr2csc if with_map else None)
         self.nblocks, self.block_docs = nblocks, block_docs
         del ws
 

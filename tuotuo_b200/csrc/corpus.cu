@@ -52,21 +52,24 @@ __global__ void split_runs_kernel(const uint64_t* __restrict__ ukeys, const int6
     }
 }
 
-// key of CSR position p = (doc(p) / block_docs) * V + word(p); doc(p) by binary search in rowptr (empty documents are
-// skipped correctly).  Also materialises doc(p) and the identity permutation for the pair sort.
-__global__ void csc_keys_kernel(const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, int64_t D,
-                                int64_t V, int64_t nnz, int64_t block_docs, uint32_t* __restrict__ keys,
-                                uint32_t* __restrict__ docs, uint32_t* __restrict__ pos)
+// key of CSR position p = (doc(p) / block_docs) * V + word(p).  One warp per document walks its row (coalesced);
+// also materialises doc(p) and the identity permutation for the pair sort.
+__global__ void __launch_bounds__(256) csc_keys_kernel(const int64_t* __restrict__ rowptr,
+                                                       const int32_t* __restrict__ colidx, int64_t D, int64_t V,
+                                                       int64_t nnz, int64_t block_docs, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ docs, uint32_t* __restrict__ pos)
 {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = D;  // last d with rowptr[d] <= p
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (rowptr[mid] <= p) lo = mid; else hi = mid;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = warp0; d < D; d += nwarps) {
+        const int64_t b = rowptr[d], e = rowptr[d + 1];
+        const uint32_t base = (uint32_t)((d / block_docs) * V);
+        for (int64_t p = b + lane; p < e; p += 32) {
+            keys[p] = base + (uint32_t)colidx[p];
+            docs[p] = (uint32_t)d;
+            pos[p] = (uint32_t)p;
         }
-        keys[p] = (uint32_t)((lo / block_docs) * V + colidx[p]);
-        docs[p] = (uint32_t)lo;
-        pos[p] = (uint32_t)p;
     }
 }
 
@@ -229,7 +232,8 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
         return TTLDA_EWORKSPACE;
     }
     if (nnz > 0) {
-        csc_keys_kernel<<<grid_1d(nnz), 256, 0, s>>>(rowptr, colidx, D, V, nnz, block_docs, w.keys, w.docs, w.pos);
+        csc_keys_kernel<<<grid_for_warps(D, 8, 16), 256, 0, s>>>(rowptr, colidx, D, V, nnz, block_docs, w.keys, w.docs,
+                                                                  w.pos);
         TTLDA_LAUNCH_CHECK("csc_keys");
         // LSD radix sort is stable: within a (block, word), CSR positions (hence documents) stay ascending.
         e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, w.keys, w.skeys, w.pos, w.spos, nnz, 0, bits_for(VV), s);

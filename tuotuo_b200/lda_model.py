@@ -257,7 +257,7 @@ class LDASmoothed:
             nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
             st.part[0, 1].copy_(st.part[4, 0])
 
-    def _commit_iteration(self):
+    def _commit_iteration(self, use_ratio: bool = True):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
         adopt the E-step's gamma / exp(E[log theta])."""
         st, c = self._st, self._st.corpus
@@ -267,13 +267,80 @@ class LDASmoothed:
             nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
         else:
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
-                          st.ratio)
+                          st.ratio if use_ratio else None)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink
         nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
         st.cur ^= 1
         self._invalidate()
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # streaming entry point: one EM iteration whose corpus arrives from (pinned) host memory
+    # ------------------------------------------------------------------------------------------------------------------
+    def em_step_from_host(self, rowptr, colidx, counts, e_num_step: int = 100, chunks: int = 16,
+                          sampling: bool = False) -> float:
+        """One EM iteration (lda_model.py:285-316 + the perplexity of the incoming state, :403-409) on a CSR corpus
+        that lives in host memory (torch CPU tensors, ideally pinned): rowptr int64[D+1], colidx/counts int32[nnz],
+        same D and V as the fitted corpus.  The upload is pipelined with the E-step: the documents are cut into
+        `chunks` nnz-balanced blocks, block i+1 crosses PCIe on a copy stream while the E-step kernel runs on block i;
+        the CSC mirror is rebuilt on the device once the last block has landed.  Returns the perplexity of the
+        incoming state on this corpus.  This is the per-step path `bench.py` times as `e2e`."""
+        from .corpus import balanced_doc_partition
+
+        st = self._st
+        if st is None:
+            raise RuntimeError("fit() first (em_num_step=0 initialises the state without iterating)")
+        if self._inner_fixed_point or self._sstats_mode != "csc":
+            raise NotImplementedError("em_step_from_host supports the default (reference-parity, csc) mode")
+        c = st.corpus
+        D = rowptr.numel() - 1
+        nnz = int(colidx.numel())
+        if D != st.D:
+            raise ValueError("the streamed corpus must have the fitted number of documents")
+        if nnz > c.colidx.numel():
+            raise ValueError("the streamed corpus has more nonzeros than the device buffers hold")
+        compute = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=st.dev)
+        cs = self._copy_stream
+        cs.wait_stream(compute)  # the previous iteration may still be reading the corpus buffers
+        rp_np = rowptr.numpy()
+        bounds = balanced_doc_partition(rp_np, max(1, int(chunks)))
+        with torch.cuda.stream(cs):
+            c.rowptr.copy_(rowptr, non_blocking=True)
+        cur, nxt = st.cur, st.cur ^ 1
+        acc = torch.zeros(nv.NPART, dtype=torch.float64, device=st.dev)
+        it_acc = torch.zeros(2, dtype=torch.int64, device=st.dev)
+        for i in range(len(bounds) - 1):
+            d0, d1 = int(bounds[i]), int(bounds[i + 1])
+            if d1 <= d0:
+                continue
+            s, e = int(rp_np[d0]), int(rp_np[d1])
+            with torch.cuda.stream(cs):
+                c.colidx[s:e].copy_(colidx[s:e], non_blocking=True)
+                c.counts[s:e].copy_(counts[s:e], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            compute.wait_event(ev)
+            nv.estep(c.rowptr[d0:d1 + 1], c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(),
+                     st.eT[cur][d0:d1], st.eB, st.gamma[cur][d0:d1], st.gamma[nxt][d0:d1], None, e_num_step, 1e-05,
+                     st.iters, st.part[0], st.ws)
+            acc += st.part[0]
+            it_acc += st.iters
+        c.nnz = nnz
+        c.build_csc(c.nblocks, c.block_docs, with_map=False)
+        nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
+        st.part[0].copy_(acc)
+        st.part[0, 1].copy_(st.part[4, 0])
+        st.iters.copy_(it_acc)
+        self.inner_iterations, capped = self._collect(tok_row=0)
+        perplexity = self._perplexity_from_terms(sampling)
+        if capped:
+            warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
+        st.part[1, 0].copy_(st.part[0, 1])
+        self._commit_iteration(use_ratio=False)  # no csr2csc map existed while the E-step ran: recompute c/N
+        return perplexity
 
     def _collect(self, tok_row: int):
         """One device->host read of the terms of the CURRENT state's ELBO (summed over ranks when sharded).
