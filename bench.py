@@ -218,7 +218,6 @@ def run_ours(args):
         lda._estep_speculative(e_num_step=100)
         lda._collect(tok_row=0)
         p = lda._perplexity_from_terms(False)
-        st.part[1, 0].copy_(st.part[0, 1])
         lda._commit_iteration()
         return p
 

@@ -254,8 +254,6 @@ class LDASmoothed:
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
                      st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
-            nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
-            st.part[0, 1].copy_(st.part[4, 0])
 
     def _commit_iteration(self, use_ratio: bool = True):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
@@ -269,8 +267,18 @@ class LDASmoothed:
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
                           st.ratio if use_ratio else None)
         dist = self._dist()
-        if dist is not None:
-            dist.all_reduce(st.sstats)  # NCCL sum of the K x V statistics over NVLink
+        work = None
+        if dist is not None:  # NCCL sum of the K x V statistics over NVLink, asynchronous:
+            work = dist.all_reduce(st.sstats, async_op=True)  # the theta refresh below overlaps it
+        # theta refresh of the state being adopted + its theta-prior ELBO term (kept in part[1][0])
+        if self._inner_fixed_point or self._fused_refresh:
+            st.part[1, 0].copy_(st.part[0, 1])  # the E-step kernel produced both
+        else:
+            nxt = st.cur ^ 1
+            nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
+            st.part[1, 0].copy_(st.part[4, 0])
+        if work is not None:
+            work.wait()
         nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
         st.cur ^= 1
         self._invalidate()
@@ -330,15 +338,12 @@ class LDASmoothed:
             it_acc += st.iters
         c.nnz = nnz
         c.build_csc(c.nblocks, c.block_docs, with_map=False)
-        nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
         st.part[0].copy_(acc)
-        st.part[0, 1].copy_(st.part[4, 0])
         st.iters.copy_(it_acc)
         self.inner_iterations, capped = self._collect(tok_row=0)
         perplexity = self._perplexity_from_terms(sampling)
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
-        st.part[1, 0].copy_(st.part[0, 1])
         self._commit_iteration(use_ratio=False)  # no csr2csc map existed while the E-step ran: recompute c/N
         return perplexity
 
@@ -432,8 +437,6 @@ class LDASmoothed:
                 return perplexities if return_perplexities else None
             if capped:
                 warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
-            # the theta-prior term of the state being adopted was produced by the E-step (record entry 1)
-            st.part[1, 0].copy_(st.part[0, 1])
             self._commit_iteration()
         # perplexity of the final state (or the initial one when em_num_step == 0)
         self._tokens()
