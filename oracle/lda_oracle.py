@@ -311,7 +311,7 @@ class OracleLDA:
     # -- lda_model.py:167-194 ------------------------------------------------------------------------------
     def approx_perplexity(self, X: CSRCorpus, sampling=False, Elogtheta=None, Elogbeta=None):
         elbo, logs = self.approx_elbo(X, sampling, Elogtheta, Elogbeta)
-        total = float(X.tokens)
+        total = np.float64(X.tokens)  # np.sum(X) in the reference: a zero token count yields inf/nan, not an exception
         if sampling:
             total = total * self.D_population / X.D  # :188
         temp = -elbo / total

@@ -476,3 +476,48 @@ def test_em_step_from_host_equals_resident_iteration(chunks):
     assert relerr(ps, pr[:3]) < 1e-12  # perplexity of the incoming state of each iteration
     assert relerr(m._gamma_, ref._gamma_) < 1e-12 and relerr(m._lambda_, ref._lambda_) < 1e-12
     assert m.inner_iterations == 2 * 900
+
+
+EDGE = [
+    # (K, V, rows as lists of (word, count))
+    (1, 1, [[(0, 3)]]),                                   # one topic, one word, one document
+    (1, 5, [[(0, 1), (4, 2)], [], [(2, 7)]]),             # K = 1 with an empty document
+    (3, 4, [[], [], []]),                                 # nothing but empty documents (nnz = 0)
+    (7, 9, [[(8, 1)]] * 40),                              # identical one-word documents: one long posting list
+    (5, 3, [[(0, 1000000), (1, 1), (2, 1)]]),             # a huge count
+    (33, 70, [[(w, 1 + (w * d) % 3) for w in range(d % 70, 70, 1 + d % 5)] for d in range(65)]),  # ld=36, ragged
+    (4, 2000, [[(w, 1) for w in range(0, 2000, 3)]] * 3),  # rows far longer than a 32-item batch
+]
+
+
+@pytest.mark.parametrize("K,V,rows", EDGE)
+@pytest.mark.parametrize("fixed_point", [False, True])
+def test_edge_cases_vs_oracle(K, V, rows, fixed_point):
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    rp = np.cumsum([0] + [len(r) for r in rows]).astype(np.int64)
+    ci = np.array([w for r in rows for w, _ in r], dtype=np.int32)
+    ct = np.array([c for r in rows for _, c in r], dtype=np.int32)
+    o = OracleLDA(K, engine="c", inner_fixed_point=fixed_point)
+    m = LDASmoothed(K, verbose=False, inner_fixed_point=fixed_point)
+    if ct.sum() == 0:
+        # an all-empty corpus: the reference divides by a zero token count; both sides must agree on nan/inf
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=2, update_hyper_parms=False)
+            pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, update_hyper_parms=False,
+                       return_perplexities=True)
+        assert len(pg) == len(po) and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+        return
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False)
+        pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    assert len(pg) == len(po)
+    if abs(o.last_elbo) > 1e-6:
+        assert relerr(m._last_elbo, o.last_elbo) < 1e-10 and relerr(pg, po) < TOL_PERP
+    else:  # K = V = 1: the ELBO is exactly 0 and the reference's exponent clip (utils.py:20-26) is discontinuous there
+        assert abs(m._last_elbo - o.last_elbo) < 1e-11
+    tol = 1e-8 if fixed_point else TOL_STATE
+    assert relerr(m._gamma_, o.gamma) < tol and relerr(m._lambda_, o.lam) < tol

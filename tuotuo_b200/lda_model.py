@@ -364,7 +364,7 @@ class LDASmoothed:
     def _perplexity_from_terms(self, sampling: bool) -> float:
         t = self._st.terms
         elbo = t["tok"] + t["theta"]  # document-dependent part (lda_model.py:125-148)
-        total = t["count"]
+        total = np.float64(t["count"])  # np.sum(X) in the reference: a zero count yields inf/nan, not an exception
         if sampling:  # lda_model.py:152-153,187-188
             scale = self.D_population / self._num_doc_global
             elbo = elbo * scale
