@@ -162,7 +162,7 @@ int ttlda_estep_fixed_point_f64(const int64_t* rowptr, const int32_t* colidx, co
  */
 int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks);
 int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts,
-                         int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks,
+                         int64_t D, int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks,
                          const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
                          double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
@@ -200,7 +200,7 @@ int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t l
  *   partial_out double[TTLDA_NPART]: [0] token term, [2] sum of counts.
  */
 int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts,
-                          int64_t D, int64_t K, int64_t ld,
+                          int64_t D, int64_t K, int64_t V, int64_t ld,
                           const double* exp_elogtheta, const double* exp_elogbeta, double* partial_out,
                           void* workspace, int64_t workspace_bytes, void* stream);
 

@@ -521,3 +521,25 @@ def test_edge_cases_vs_oracle(K, V, rows, fixed_point):
         assert abs(m._last_elbo - o.last_elbo) < 1e-11
     tol = 1e-8 if fixed_point else TOL_STATE
     assert relerr(m._gamma_, o.gamma) < tol and relerr(m._lambda_, o.lam) < tol
+
+
+@pytest.mark.parametrize("K", [70, 100, 128])
+def test_tma_gather4_variants_are_exact(monkeypatch, K):
+    """TTLDA_TMA=1: K-vector rows fed by the TMA engine (cp.async.bulk.tensor ... tile::gather4 + mbarrier pipeline)
+    in the E-step, the ELBO pass and the statistics pass; same answers as the oracle."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    V = 900
+    rp, ci, ct = numpy_corpus(700 + K, 300, V, 25, 70, ragged=True)
+    o = OracleLDA(K, engine="c")
+    po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=3)
+    monkeypatch.setenv("TTLDA_TMA", "1")
+    m = LDASmoothed(K, verbose=False)
+    pg = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert relerr(pg, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+    monkeypatch.setenv("TTLDA_FUSED_REFRESH", "1")  # MODE 1 kernel as well
+    m2 = LDASmoothed(K, verbose=False)
+    p2 = m2.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert relerr(p2, po) < TOL_PERP and relerr(m2._gamma_, o.gamma) < TOL_STATE

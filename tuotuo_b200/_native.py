@@ -42,13 +42,14 @@ SIGNATURES = {
                                                    _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_sstats_atomic_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
-    "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
-                                            _ptr, _i64, _ptr]),
+    "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                            _ptr, _ptr, _i64, _ptr]),
     "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
                                               _ptr]),
-    "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
+                                             _ptr]),
     "ttlda_hyper_stats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
     "ttlda_psi_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
     "ttlda_transpose_pad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr]),
@@ -226,7 +227,8 @@ def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, 
     global kernel_count
     ld = eT.shape[1]
     kernel_count += 1 if nblocks > 1 else 0  # + sstats_fold_kernel
-    _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), int(V), int(K), ld, int(nnz),
+    _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), eT.shape[0], int(V), int(K), ld,
+          int(nnz),
           int(nblocks), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
@@ -254,7 +256,8 @@ def beta_refresh(lam, K, eta, eB, elogbeta, colsum, partial, ws):
 
 def elbo_tokens(rowptr, colidx, counts, K, eT, eB, partial, ws):
     D, ld = eT.shape
-    _call("ttlda_elbo_tokens_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), ld, _p(eT, f64),
+    _call("ttlda_elbo_tokens_f64", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), D, int(K), eB.shape[0], ld,
+          _p(eT, f64),
           _p(eB, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 

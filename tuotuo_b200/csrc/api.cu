@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "ttlda_common.cuh"
+#include "tma_gather.cuh"
 
 namespace ttlda {
 
@@ -61,6 +62,38 @@ __global__ void transpose_kernel(const double* __restrict__ src, int64_t rows, i
         int64_t c = c0 + i, r = r0 + threadIdx.x;  // dst row = c, dst col = r
         if (c < cols && r < dst_ld) dst[c * dst_ld + r] = tile[threadIdx.x][i];  // r >= rows reads zeros (padding)
     }
+}
+
+// Tensor map of a [rows][ld] fp64 table for tile::gather4 loads: 2-D, box {ld, 1} (one row per gathered index), no
+// swizzle / interleave.  The driver's encoder is reached through the runtime (no libcuda link dependency).
+int make_row_gather_map(const double* table, int64_t rows, int64_t ld, CUtensorMap* out)
+{
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        if (e != cudaSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled not available (%s)", cudaGetErrorString(e));
+            return TTLDA_ECUDA;
+        }
+        encode = (EncodeFn)fn;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)ld, (cuuint64_t)(rows > 0 ? rows : 1)};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ld * 8};
+    const cuuint32_t box[2] = {(cuuint32_t)ld, 1};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(table), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld][%lld] table", (int)r, (long long)rows, (long long)ld);
+        return TTLDA_ECUDA;
+    }
+    return TTLDA_OK;
 }
 
 }  // namespace ttlda

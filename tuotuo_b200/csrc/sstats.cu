@@ -20,7 +20,7 @@
 // postings of word w inside document block b, so that consecutive chunks gather eT rows from one block-sized
 // window of the D x K table that stays resident in the 126 MB L2; the per-block partial statistics are summed in
 // block order by sstats_fold_kernel.  Bound: gather of 8K bytes per nonzero (HBM unblocked, L2 blocked).
-#include "traverse.cuh"
+#include "tma_gather.cuh"
 
 namespace ttlda {
 
@@ -154,6 +154,104 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
     }
 }
 
+// The ratio variant fed by the TMA engine (tma_gather.cuh): one gather4 per sub-batch lands 4 exp(E[log theta]) rows in
+// shared memory, kTmaStages sub-batches ahead, continuously across a segment's 32-item batches.  G = 8 only.
+template <int E>
+__global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __grid_constant__ CUtensorMap map,
+                                                                     const SStatsParams P)
+{
+    constexpr int G = 8, R = 4;
+    constexpr int LDP = 2 * G * E;
+    constexpr int MMAX = (LDP + 31) / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* wbase = smem_raw + (size_t)(threadIdx.x >> 5) * Gather4Pipe<E>::bytes_per_warp(P.ld);
+
+    const int lane = threadIdx.x & 31;
+    const int g = lane % G, r = lane / G;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int ld = (int)P.ld;
+    const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
+    const uint64_t pol = l2_evict_first_policy();
+
+    Gather4Pipe<E> pipe;
+    pipe.init(wbase, ld, lane);
+    double* wbuf = reinterpret_cast<double*>(wbase);  // the segment epilogue's transpose buffer aliases the drained stages
+
+    for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
+        const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
+        int64_t lo = 0, hi = P.VV;  // warp-cooperative 32-ary search for the first word with colptr[w+1] > cb
+        while (hi - lo > 1) {
+            const int64_t step = (hi - lo + 31) >> 5;
+            int64_t wi = lo + (int64_t)(lane + 1) * step - 1;
+            if (wi > hi - 1) wi = hi - 1;
+            const unsigned hit = __ballot_sync(0xffffffffu, P.colptr[wi + 1] > cb);
+            const int j = __ffs(hit) - 1;
+            const int64_t wj = lo + (int64_t)(j + 1) * step - 1;
+            const int64_t new_hi = ((wj > hi - 1) ? hi - 1 : wj) + 1;
+            if (j > 0) lo = lo + (int64_t)j * step;
+            hi = new_hi;
+        }
+        int64_t w = lo;
+        if (lane == 0) {
+            P.carry_word[c * 2 + 0] = -1;
+            P.carry_word[c * 2 + 1] = -1;
+        }
+        int64_t pos = cb;
+        while (pos < ce) {
+            int64_t wb = P.colptr[w], we = P.colptr[w + 1];
+            while (we <= pos) {
+                ++w;
+                wb = we;
+                we = P.colptr[w + 1];
+            }
+            const int64_t se = (we < ce) ? we : ce;
+            KSlice<G, E> acc;
+            acc.zero();
+            double r_cur = 0., r_nxt = 0.;
+            const int64_t n = se - pos;
+            tma_walk<E>(
+                pipe, &map, P.docidx + pos, n, lane, g, r, last_ok, pol,
+                [&](int64_t base) { r_nxt = (base + lane < n) ? ld_stream_f64(P.ratio + pos + base + lane, pol) : 0.; },
+                [&]() { r_cur = r_nxt; },
+                [&](int sb, const KSlice<G, E>& row) { acc.axpy(__shfl_sync(0xffffffffu, r_cur, sb * R + r), row); },
+                [](int) {});
+            acc.to_smem(wbuf + r * LDP, g);
+            __syncwarp();
+            const bool whole = (pos == wb) && (se == we);
+            const int slot = (pos != wb) ? 0 : 1;
+            double* dst = whole ? P.S + w * P.ld : P.carry + (c * 2 + slot) * P.ld;
+#pragma unroll
+            for (int m = 0; m < MMAX; ++m) {
+                const int k = lane + 32 * m;
+                if (k < ld) {
+                    double a = 0.;
+#pragma unroll
+                    for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
+                    st_stream_f64(dst + k, a, pol);
+                }
+            }
+            __syncwarp();
+            if (!whole && lane == 0) P.carry_word[c * 2 + slot] = (int32_t)w;
+            pos = se;
+            if (se == we) ++w;
+        }
+    }
+}
+
+template <int E>
+static int launch_sstats_tma(const SStatsParams& P, int grid, int64_t table_rows, cudaStream_t s)
+{
+    CUtensorMap map;
+    int rc = make_row_gather_map(P.eT, table_rows, P.ld, &map);
+    if (rc != TTLDA_OK) return rc;
+    const size_t smem = (kWordThreads / 32) * Gather4Pipe<E>::bytes_per_warp(P.ld);
+    cudaError_t e = cudaFuncSetAttribute(sstats_tma_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(sstats_tma)");
+    sstats_tma_kernel<E><<<grid, kWordThreads, smem, s>>>(map, P);
+    return TTLDA_OK;
+}
+
 // Sum the carries of each cut word in chunk order.  One warp per chunk whose TAIL slot is in use (= the chunk in
 // which a cut word starts); it walks the following chunks' HEAD slots while they name the same word.
 __global__ void __launch_bounds__(256) sstats_carry_kernel(const SStatsParams P)
@@ -240,13 +338,13 @@ int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t
     return (int64_t)b;
 }
 
-int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t V, int64_t K,
-                         int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
+int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t D, int64_t V,
+                         int64_t K, int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
                          const double* exp_elogbeta, const double* ratio_csc, double* sstats, void* workspace,
                          int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(colptr && exp_elogtheta && (exp_elogbeta || ratio_csc) && sstats && workspace, "NULL pointer");
-    TTLDA_REQUIRE(V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
+    TTLDA_REQUIRE(D >= 0 && V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
     TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
     TTLDA_REQUIRE(nblocks >= 1 && nblocks * V < ((int64_t)1 << 31), "bad nblocks");
     if (workspace_bytes < ttlda_sstats_workspace_bytes(nnz, V, ld, nblocks)) {
@@ -281,6 +379,17 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
         if (G == 2 || G == 4 || G == 8 || G == 16 || G == 32) gs = {G, (int)((ld + 2 * G - 1) / (2 * G))};
     }
     bool launched = false;
+    if (ratio_csc && tma_gather_applicable(gs.G, ld) && tma_gather_enabled() && D > 0) {  // rows fed by TMA gather4
+        int rc = TTLDA_OK;
+        switch (gs.E) {
+            case 5: rc = launch_sstats_tma<5>(P, grid, D, s); launched = true; break;
+            case 6: rc = launch_sstats_tma<6>(P, grid, D, s); launched = true; break;
+            case 7: rc = launch_sstats_tma<7>(P, grid, D, s); launched = true; break;
+            case 8: rc = launch_sstats_tma<8>(P, grid, D, s); launched = true; break;
+            default: break;
+        }
+        if (rc != TTLDA_OK) return rc;
+    }
 #define TTLDA_CASE(GG, EE)                        \
     if (!launched && gs.G == GG && gs.E == EE) {  \
         launch_shape<GG, EE>(P, grid, s);         \
