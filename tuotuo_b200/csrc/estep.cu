@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 const int c = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt: the group idles harmlessly
                 const double p = group_sum<G>(t.dot(row));
                 if (ESTEP) {
-                    const double rr = (double)c / (p + 1e-100);
+                    const double rr = fast_div_pos((double)c, p + 1e-100);
                     acc.axpy(rr, row);
                 }
                 // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kDocThreads, 4) doc_pass_tma_kernel(const __gr
             [&](int sb, const KSlice<G, E>& row) {
                 const int c = __shfl_sync(0xffffffffu, c_cur, sb * R + r);  // 0 past the end: the group idles
                 const double p = group_sum<G>(t.dot(row));
-                if (ESTEP) acc.axpy((double)c / (p + 1e-100), row);  // lda_model.py:242,248
+                if (ESTEP) acc.axpy(fast_div_pos((double)c, p + 1e-100), row);  // lda_model.py:242,248
                 // hand p back to the lane that loaded nonzero `lane` of the batch (group lane % R, sub-batch lane / R)
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == sb) my_p = pv;

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                     } else {
                         const int cc = __shfl_sync(0xffffffffu, my_c, s * R + r);  // 0 past the end of the segment
                         const double p = group_sum<G>(b.dot(row));
-                        acc.axpy((double)cc / (p + 1e-100), row);  // lda_model.py:242,262
+                        acc.axpy(fast_div_pos((double)cc, p + 1e-100), row);  // lda_model.py:242,262
                     }
                 });
             }

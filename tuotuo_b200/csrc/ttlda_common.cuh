@@ -136,6 +136,19 @@ __device__ __forceinline__ double psi_exact(double x)
     return log(x) - 0.5 / x - z * p + shift;
 }
 
+// c / x for a normal positive x, without the IEEE division's special-case path: hardware reciprocal approximation
+// (MUFU.RCP64H, ~2^-23) + two Newton steps + the multiply = 5 dependent FP64 operations instead of ~9 plus a branch.
+// Result within ~2 ulp of the correctly rounded quotient — the parity budget on gamma / lambda is 1e-9 relative.
+// The division sits on the critical path of every sub-batch (tools/membench2.cu: +24 % when it is added).
+__device__ __forceinline__ double fast_div_pos(double c, double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-x, y, 2.);
+    y = y * fma(-x, y, 2.);
+    return c * y;
+}
+
 // 16-byte global loads of a K-vector slice.  The beta tables are re-read by many documents: keep them on the
 // read-only path; streaming data (CSR arrays) goes through L1::no_allocate.
 __device__ __forceinline__ double2 ldg2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
