@@ -127,8 +127,15 @@ def cpu_port_iteration_time(rp, ci, ct, K, V, steps, warmup):
     """Seconds per full EM iteration (E-step + M-step + ELBO/perplexity) of the CPU oracle on the given CSR sample."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import numpy as np
-    from lda_oracle import CSRCorpus, OracleLDA, c_num_threads
+    from lda_oracle import CSRCorpus, OracleLDA, c_num_threads, c_set_num_threads
 
+    # all the host threads this process may use — torchrun exports OMP_NUM_THREADS=1, which must not throttle the
+    # CPU baseline
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    c_set_num_threads(ncpu)
     X = CSRCorpus(rp, ci, ct, V)
     m = OracleLDA(K, engine="c")
     m.M, m.V = X.D, V
@@ -292,7 +299,7 @@ def run_ours(args):
                 "note": "gathers of the 8*K*V-byte exp(E[log beta]) table are L2 hits when it fits the 126 MB L2"}
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:  # reported at N=1 only (bench contract)
         n = min(c.D, args.cpu_docs)
         rp = c.rowptr[:n + 1].cpu().numpy()
         e = int(rp[-1])
