@@ -325,8 +325,9 @@ def run_ours(args):
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 48 * world,
                         "ms_per_step": e2e_ms, "steps": n_e2e,
-                        "what": "LDASmoothed.em_step_from_host: pinned-host CSR -> device (chunked, overlapped with the "
-                                "E-step), CSC rebuild, statistics, M-step, perplexity terms -> host"},
+                        "what": "LDASmoothed.em_step_from_host: pinned-host CSR -> device one document block at a time; "
+                                "per block CSC mirror + E-step + statistics overlap the next block's upload; then "
+                                "fold, theta refresh, M-step, perplexity terms -> host"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "perplexity_trace": [round(p, 6) for p in perps[:8]]}
         print(json.dumps(line), flush=True)

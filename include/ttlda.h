@@ -87,6 +87,18 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
                      int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* One document block of a document-blocked mirror, built on its own (streaming ingestion: block b can be mirrored,
+ * E-stepped and accumulated while block b+1 is still crossing PCIe).  The block holds documents
+ * [doc_base, doc_base + D_block) whose entries occupy positions [pos_base, pos_base + nnz_block) of the corpus-wide
+ * CSR arrays AND of the corpus-wide mirror arrays (blocks are contiguous in both).  rowptr_block = &rowptr[doc_base]
+ * (D_block + 1 absolute offsets); colidx/counts/docidx/ccounts/csr2csc are the corpus-wide array bases;
+ * colptr_block = &colptr[b * V] (V + 1 absolute offsets are written).  The result is identical to the block's slice
+ * of ttlda_csr_to_csc(nblocks, block_docs = D_block).  Workspace: ttlda_csr_to_csc_workspace_bytes(nnz_block,..,1). */
+int ttlda_csr_to_csc_block(const int64_t* rowptr_block, const int32_t* colidx, const int32_t* counts,
+                           int64_t D_block, int64_t V, int64_t doc_base, int64_t pos_base, int64_t nnz_block,
+                           int64_t* colptr_block, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /*
  * theta refresh: exp_elogtheta = exp(dirichlet_expectation(gamma)) and the theta-prior ELBO term.
  * Replaces: _dirichlet_expectation_2d(self._gamma_) at tuotuo/lda_model.py:116,256 (+ np.exp at :232) and
@@ -166,6 +178,19 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
                          const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
                          double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* The same pass over ONE document block of a blocked mirror (built by ttlda_csr_to_csc_block or a slice of
+ * ttlda_csr_to_csc): colptr_block = &colptr[b * V] (absolute offsets), docidx / ccounts / ratio_csc / exp_elogtheta
+ * are the corpus-wide bases, sstats_block [V][ld] receives the block's partial statistics;
+ * ttlda_sstats_fold_f64 then sums the nblocks partials [nblocks][V][ld] in block order into sstats [V][ld] —
+ * bit-identical to the one-call form.  Workspace: ttlda_sstats_workspace_bytes(nnz_block, V, ld, 1). */
+int ttlda_sstats_csc_block_f64(const int64_t* colptr_block, const int32_t* docidx, const int32_t* ccounts,
+                               int64_t D, int64_t V, int64_t K, int64_t ld, int64_t pos_base, int64_t nnz_block,
+                               const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
+                               double* sstats_block,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+int ttlda_sstats_fold_f64(const double* sstats_blocks, int64_t nblocks, int64_t V, int64_t ld, double* sstats,
+                          void* stream);
 
 /* One-pass alternative to ttlda_sstats_csc_f64 (the north-star's literal formulation): document-major scatter of
  * eT[d,k]*c/N into sstats[w,k] with red.global.add.f64.  Same result up to summation order (NOT bit-reproducible);

@@ -455,27 +455,93 @@ def test_ratio_handoff_and_recompute_agree(monkeypatch):
     assert relerr(res["1"][1], res["0"][1]) < 1e-12 and relerr(res["1"][2], res["0"][2]) < 1e-12
 
 
-@pytest.mark.parametrize("chunks", [1, 3, 8])
-def test_em_step_from_host_equals_resident_iteration(chunks):
-    """Streaming entry point: corpus arrives from pinned host memory in document chunks overlapped with the E-step;
-    results equal the resident-corpus iterations of fit()."""
+@pytest.mark.parametrize("blocks", [1, 3, 8])
+@pytest.mark.parametrize("handoff", ["1", "0"])
+def test_em_step_from_host_equals_resident_iteration(monkeypatch, blocks, handoff):
+    """Streaming entry point: the corpus arrives from pinned host memory one document block at a time, each block
+    mirrored / E-stepped / accumulated while the next one is in flight; results equal the resident-corpus iterations
+    of fit() — bit for bit (same segments, same summation order)."""
     from tuotuo.document import Document
     from tuotuo.lda_model import LDASmoothed
     from tuotuo_b200.synth import numpy_corpus
 
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", str(blocks))
+    monkeypatch.setenv("TTLDA_RATIO_HANDOFF", handoff)
     rp, ci, ct = numpy_corpus(61, 900, 600, 20, 50, ragged=True)
     ref = LDASmoothed(40, verbose=False)
     pr = ref.fit(Document.from_csr(rp, ci, ct, 600), em_num_step=3, update_hyper_parms=False, return_perplexities=True)
     m = LDASmoothed(40, verbose=False)
     m.fit(Document.from_csr(rp, ci, ct, 600), em_num_step=0, update_hyper_parms=False)
+    c = m._st.corpus
+    assert c.nblocks == blocks
     h = [torch.as_tensor(a).pin_memory() for a in (rp, ci, ct)]
-    # scribble over the device corpus: the streamed copy must be what the iteration reads
-    m._st.corpus.colidx.zero_()
-    m._st.corpus.counts.zero_()
-    ps = [m.em_step_from_host(*h, chunks=chunks) for _ in range(3)]
-    assert relerr(ps, pr[:3]) < 1e-12  # perplexity of the incoming state of each iteration
-    assert relerr(m._gamma_, ref._gamma_) < 1e-12 and relerr(m._lambda_, ref._lambda_) < 1e-12
+    mirror = [t.clone() for t in (c.colptr, c.docidx, c.ccounts, c.csr2csc)]
+    # scribble over the device corpus and its mirror: the streamed copy must be what the iteration reads
+    for t in (c.colidx, c.counts, c.docidx, c.ccounts, c.csr2csc, c.colptr):
+        t.fill_(-1)
+    ps = [m.em_step_from_host(*h) for _ in range(3)]
+    for a, b in zip(mirror[:3] + (mirror[3:] if handoff == "1" else []),
+                    [c.colptr, c.docidx, c.ccounts] + ([c.csr2csc] if handoff == "1" else [])):
+        assert torch.equal(a, b)  # block-by-block mirror == one-call blocked mirror
+    assert relerr(ps, pr[:3]) < 1e-13  # perplexity of the incoming state of each iteration
+    assert np.array_equal(m._gamma_, ref._gamma_) and np.array_equal(m._lambda_, ref._lambda_)
     assert m.inner_iterations == 2 * 900
+
+
+def test_block_entry_points_equal_one_call_forms(nv, dev):
+    """ttlda_csr_to_csc_block / ttlda_sstats_csc_block_f64 + ttlda_sstats_fold_f64 over every block reproduce
+    ttlda_csr_to_csc / ttlda_sstats_csc_f64 with nblocks > 1 exactly (blocks that do not start on the chunk grid,
+    an empty block, with and without the c/N ratios)."""
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(7, 1300, 300, 5, 60, ragged=True)
+    D, V, K = 1300, 300, 20
+    ld = nv.ld_for(K)
+    bd = 300
+    nb = -(-D // bd)
+    lens = np.diff(rp)
+    lens[bd:2 * bd] = 0  # a second corpus whose block 1 is empty
+    rp2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    keep = np.ones(len(ci), bool)
+    keep[rp[bd]:rp[2 * bd]] = False
+    ci2, ct2 = ci[keep], ct[keep]
+    for rowptr, colidx, counts in ((rp, ci, ct), (rp2, ci2, ct2)):
+        nnz = len(colidx)
+        t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+        d_rp, d_ci, d_ct = t(rowptr), t(colidx), t(counts)
+        i32 = dict(dtype=torch.int32, device=dev)
+        ref = [torch.empty(nb * V + 1, dtype=torch.int64, device=dev), torch.empty(nnz, **i32), torch.empty(nnz, **i32),
+               torch.empty(nnz, **i32)]
+        ws = torch.empty(nv.csr_to_csc_workspace_bytes(nnz, D, V, nb), dtype=torch.uint8, device=dev)
+        nv.csr_to_csc(d_rp, d_ci, d_ct, D, V, nnz, nb, bd, ref[0], ref[1], ref[2], ws, ref[3])
+        blk = [torch.full_like(x, -7) for x in ref]
+        for b in range(nb):
+            d0, d1 = b * bd, min((b + 1) * bd, D)
+            s, e = int(rowptr[d0]), int(rowptr[d1])
+            nv.csr_to_csc_block(d_rp[d0:d1 + 1], d_ci, d_ct, V, d0, s, e - s, blk[0][b * V:b * V + V + 1], blk[1], blk[2],
+                                ws, blk[3])
+        for a, b_ in zip(ref, blk):
+            assert torch.equal(a, b_)
+
+        g = torch.Generator(device="cpu").manual_seed(3)
+        eT = torch.zeros((D, ld), dtype=torch.float64)
+        eT[:, :K] = torch.rand((D, K), generator=g, dtype=torch.float64) + 0.1
+        eB = torch.zeros((V, ld), dtype=torch.float64)
+        eB[:, :K] = torch.rand((V, K), generator=g, dtype=torch.float64) + 0.1
+        eT, eB = eT.to(dev), eB.to(dev)
+        ratio = (torch.rand(max(nnz, 1), generator=g, dtype=torch.float64) + 0.5).to(dev)
+        ws_s = torch.empty(nv.sstats_workspace_bytes(nnz, V, ld, nb), dtype=torch.uint8, device=dev)
+        for r in (None, ratio):
+            S_ref = torch.empty((V, ld), dtype=torch.float64, device=dev)
+            nv.sstats_csc(ref[0], ref[1], ref[2], V, K, nnz, nb, eT, eB, S_ref, ws_s, r)
+            Sb = torch.full((nb, V, ld), float("nan"), dtype=torch.float64, device=dev)
+            for b in range(nb):
+                d0, d1 = b * bd, min((b + 1) * bd, D)
+                s, e = int(rowptr[d0]), int(rowptr[d1])
+                nv.sstats_csc_block(ref[0][b * V:b * V + V + 1], ref[1], ref[2], V, K, s, e - s, eT, eB, Sb[b], ws_s, r)
+            S = torch.empty_like(S_ref)
+            nv.sstats_fold(Sb, S)
+            assert torch.equal(S, S_ref)
 
 
 EDGE = [

@@ -34,6 +34,8 @@ SIGNATURES = {
     "ttlda_csr_to_csc_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_csr_to_csc": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr,
                                         _i64, _ptr]),
+    "ttlda_csr_to_csc_block": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
+                                              _ptr, _i64, _ptr]),
     "ttlda_reduce_workspace_bytes": (_i64, []),
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
@@ -44,6 +46,9 @@ SIGNATURES = {
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
                                             _ptr, _ptr, _i64, _ptr]),
+    "ttlda_sstats_csc_block_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                                  _ptr, _ptr, _i64, _ptr]),
+    "ttlda_sstats_fold_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
     "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
@@ -69,9 +74,9 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 # hand-written kernels launched by each entry point (CUB sort/RLE passes and memsets are not counted)
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
-    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2,
+    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2,
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
-    "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1,
+    "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
@@ -195,6 +200,14 @@ def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, d
           _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
+def csr_to_csc_block(rowptr_block, colidx, counts, V, doc_base, pos_base, nnz_block, colptr_block, docidx, ccounts, ws,
+                     csr2csc=None):
+    """One document block of a blocked mirror; colidx/counts/docidx/ccounts/csr2csc are the corpus-wide arrays."""
+    _call("ttlda_csr_to_csc_block", _p(rowptr_block, i64), _p(colidx, i32), _p(counts, i32), rowptr_block.numel() - 1,
+          int(V), int(doc_base), int(pos_base), int(nnz_block), _p(colptr_block, i64), _p(docidx, i32),
+          _p(ccounts, i32), _p(csr2csc, torch.int32), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
 def theta_refresh(gamma, K, alpha_vec, alpha_sum, eT, partial, ws):
     D, ld = gamma.shape
     _call("ttlda_theta_refresh_f64", _p(gamma, f64), D, int(K), ld, _p(alpha_vec, f64), float(alpha_sum), _p(eT, f64),
@@ -230,6 +243,19 @@ def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, 
     _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), eT.shape[0], int(V), int(K), ld,
           int(nnz),
           int(nblocks), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def sstats_csc_block(colptr_block, docidx, ccounts, V, K, pos_base, nnz_block, eT, eB, sstats_block, ws, ratio_csc=None):
+    """Statistics of one document block ([V][ld] partial); docidx/ccounts/ratio_csc/eT are the corpus-wide arrays."""
+    ld = eT.shape[1]
+    _call("ttlda_sstats_csc_block_f64", _p(colptr_block, i64), _p(docidx, i32), _p(ccounts, i32), eT.shape[0], int(V),
+          int(K), ld, int(pos_base), int(nnz_block), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats_block, f64),
+          _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def sstats_fold(sstats_blocks, sstats):
+    nb, V, ld = sstats_blocks.shape
+    _call("ttlda_sstats_fold_f64", _p(sstats_blocks, f64), nb, V, ld, _p(sstats, f64), _stream())
 
 
 def sstats_atomic(rowptr, colidx, counts, K, V, eT, eB, sstats):

@@ -56,18 +56,21 @@ __global__ void split_runs_kernel(const uint64_t* __restrict__ ukeys, const int6
 // also materialises doc(p) and the identity permutation for the pair sort.
 __global__ void __launch_bounds__(256) csc_keys_kernel(const int64_t* __restrict__ rowptr,
                                                        const int32_t* __restrict__ colidx, int64_t D, int64_t V,
-                                                       int64_t nnz, int64_t block_docs, uint32_t* __restrict__ keys,
+                                                       int64_t nnz, int64_t block_docs, int64_t doc_base,
+                                                       int64_t pos_base, uint32_t* __restrict__ keys,
                                                        uint32_t* __restrict__ docs, uint32_t* __restrict__ pos)
 {
+    // doc_base / pos_base != 0: rowptr is a slice of a larger CSR (ttlda_csr_to_csc_block) — document d of the slice is
+    // document doc_base + d of the corpus, its entries sit at absolute positions rowptr[d].. = pos_base + local
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t d = warp0; d < D; d += nwarps) {
-        const int64_t b = rowptr[d], e = rowptr[d + 1];
+        const int64_t b = rowptr[d] - pos_base, e = rowptr[d + 1] - pos_base;
         const uint32_t base = (uint32_t)((d / block_docs) * V);
         for (int64_t p = b + lane; p < e; p += 32) {
             keys[p] = base + (uint32_t)colidx[p];
-            docs[p] = (uint32_t)d;
+            docs[p] = (uint32_t)(doc_base + d);
             pos[p] = (uint32_t)p;
         }
     }
@@ -77,18 +80,19 @@ __global__ void __launch_bounds__(256) csc_keys_kernel(const int64_t* __restrict
 // VV = nblocks * V virtual words
 __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ spos,
                                   const uint32_t* __restrict__ docs, const int32_t* __restrict__ counts, int64_t VV,
-                                  int64_t nnz, int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
-                                  int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
+                                  int64_t nnz, int64_t pos_base, int64_t* __restrict__ colptr,
+                                  int32_t* __restrict__ docidx, int32_t* __restrict__ ccounts,
+                                  uint32_t* __restrict__ csr2csc)
 {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= nnz; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t wcur = (i < nnz) ? (int64_t)skeys[i] : VV;
         const int64_t wprev = (i > 0) ? (int64_t)skeys[i - 1] : -1;
-        for (int64_t w = wprev + 1; w <= wcur; ++w) colptr[w] = i;
+        for (int64_t w = wprev + 1; w <= wcur; ++w) colptr[w] = pos_base + i;
         if (i < nnz) {
             const int64_t p = spos[i];
             docidx[i] = (int32_t)docs[p];
             ccounts[i] = counts[p];
-            if (csr2csc) csr2csc[p] = (uint32_t)i;  // where CSR position p lives in the mirror
+            if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + i);  // where CSR position p lives in the mirror
         }
     }
 }
@@ -212,6 +216,33 @@ int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int6
     return (int64_t)w.total;
 }
 
+static int csr_to_csc_impl(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
+                           int64_t nnz, int64_t nblocks, int64_t block_docs, int64_t doc_base, int64_t pos_base,
+                           int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc, void* workspace,
+                           int64_t workspace_bytes, cudaStream_t s)
+{
+    const int64_t VV = nblocks * V;
+    CscWs w;
+    cudaError_t e = csc_layout(nnz, VV, (char*)workspace, w);
+    if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc layout");
+    if ((int64_t)w.total > workspace_bytes) {
+        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
+        return TTLDA_EWORKSPACE;
+    }
+    if (nnz > 0) {
+        csc_keys_kernel<<<grid_for_warps(D, 8, 16), 256, 0, s>>>(rowptr, colidx, D, V, nnz, block_docs, doc_base,
+                                                                  pos_base, w.keys, w.docs, w.pos);
+        TTLDA_LAUNCH_CHECK("csc_keys");
+        // LSD radix sort is stable: within a (block, word), CSR positions (hence documents) stay ascending.
+        e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, w.keys, w.skeys, w.pos, w.spos, nnz, 0, bits_for(VV), s);
+        if (e != cudaSuccess) return cuda_fail(e, "radix sort (csc)");
+    }
+    csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, w.docs, counts, VV, nnz, pos_base, colptr,
+                                                       docidx, ccounts, csr2csc);
+    TTLDA_LAUNCH_CHECK("csc_gather");
+    return TTLDA_OK;
+}
+
 int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
                      int64_t nnz, int64_t nblocks, int64_t block_docs, int64_t* colptr, int32_t* docidx,
                      int32_t* ccounts, uint32_t* csr2csc, void* workspace, int64_t workspace_bytes, void* stream)
@@ -222,27 +253,26 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
     TTLDA_REQUIRE(nnz < ((int64_t)1 << 32), "nnz per device must be < 2^32");
     TTLDA_REQUIRE(nblocks >= 1 && block_docs >= 1 && nblocks * block_docs >= D, "document blocks must cover D");
     TTLDA_REQUIRE(nblocks * V < ((int64_t)1 << 31), "nblocks * V must be < 2^31");
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t VV = nblocks * V;
-    CscWs w;
-    cudaError_t e = csc_layout(nnz, VV, (char*)workspace, w);
-    if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc layout");
-    if ((int64_t)w.total > workspace_bytes) {
-        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
-        return TTLDA_EWORKSPACE;
-    }
-    if (nnz > 0) {
-        csc_keys_kernel<<<grid_for_warps(D, 8, 16), 256, 0, s>>>(rowptr, colidx, D, V, nnz, block_docs, w.keys, w.docs,
-                                                                  w.pos);
-        TTLDA_LAUNCH_CHECK("csc_keys");
-        // LSD radix sort is stable: within a (block, word), CSR positions (hence documents) stay ascending.
-        e = cub::DeviceRadixSort::SortPairs(w.cub, w.cub_bytes, w.keys, w.skeys, w.pos, w.spos, nnz, 0, bits_for(VV), s);
-        if (e != cudaSuccess) return cuda_fail(e, "radix sort (csc)");
-    }
-    csc_gather_kernel<<<grid_1d(nnz + 1), 256, 0, s>>>(w.skeys, w.spos, w.docs, counts, VV, nnz, colptr, docidx,
-                                                       ccounts, csr2csc);
-    TTLDA_LAUNCH_CHECK("csc_gather");
-    return TTLDA_OK;
+    return csr_to_csc_impl(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, 0, 0, colptr, docidx, ccounts, csr2csc,
+                           workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_csr_to_csc_block(const int64_t* rowptr_block, const int32_t* colidx, const int32_t* counts, int64_t D_block,
+                           int64_t V, int64_t doc_base, int64_t pos_base, int64_t nnz_block, int64_t* colptr_block,
+                           int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc, void* workspace,
+                           int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(rowptr_block && colptr_block && workspace, "NULL pointer");
+    TTLDA_REQUIRE(nnz_block == 0 || (colidx && counts && docidx && ccounts), "NULL pointer");
+    TTLDA_REQUIRE(nnz_block >= 0 && D_block >= 0 && V >= 0 && doc_base >= 0 && pos_base >= 0, "negative size");
+    TTLDA_REQUIRE(pos_base + nnz_block < ((int64_t)1 << 32), "nnz per device must be < 2^32");
+    TTLDA_REQUIRE(doc_base + D_block < ((int64_t)1 << 31), "documents per device must be < 2^31");
+    TTLDA_REQUIRE(V < ((int64_t)1 << 31), "V must be < 2^31");
+    // the block's entries occupy [pos_base, pos_base + nnz_block) of the corpus-wide arrays, in CSR and mirror alike
+    return csr_to_csc_impl(rowptr_block, colidx ? colidx + pos_base : colidx, counts ? counts + pos_base : counts, D_block,
+                           V, nnz_block, 1, D_block > 0 ? D_block : 1, doc_base, pos_base, colptr_block,
+                           docidx ? docidx + pos_base : docidx, ccounts ? ccounts + pos_base : ccounts,
+                           csr2csc ? csr2csc + pos_base : csr2csc, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -35,7 +35,8 @@ struct SStatsParams {
     int64_t VV;
     int K;
     int64_t ld;
-    int64_t nnz;
+    int64_t pos_base;  // mirror positions [pos_base, pos_end) are processed, cut into nchunks chunks (pos_base != 0:
+    int64_t pos_end;   // one document block of a corpus-wide mirror, ttlda_sstats_csc_block_f64)
     int64_t nchunks;
     const double* eT;
     const double* eB;
@@ -65,7 +66,10 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
     const uint64_t pol = l2_evict_first_policy();
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
-        const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
+        // chunks sit on the corpus-wide grid of kChunk positions (so a block processed on its own cuts its words exactly
+        // where the one-call pass over the whole mirror does => identical bits)
+        const int64_t cg = (P.pos_base / kChunk + c) * kChunk;
+        const int64_t cb = (cg > P.pos_base) ? cg : P.pos_base, ce = (cg + kChunk < P.pos_end) ? cg + kChunk : P.pos_end;
         // first virtual word with colptr[w+1] > cb: warp-cooperative 32-ary search (4 dependent loads for 10^6 words
         // instead of 20 — the chunk's start-up latency is not hidden by anything else in this warp)
         int64_t lo = 0, hi = P.VV;  // the answer lies in [lo, hi); colptr[VV] = nnz > cb
@@ -179,7 +183,10 @@ __global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __gri
     double* wbuf = reinterpret_cast<double*>(wbase);  // the segment epilogue's transpose buffer aliases the drained stages
 
     for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
-        const int64_t cb = c * kChunk, ce = (cb + kChunk < P.nnz) ? cb + kChunk : P.nnz;
+        // chunks sit on the corpus-wide grid of kChunk positions (so a block processed on its own cuts its words exactly
+        // where the one-call pass over the whole mirror does => identical bits)
+        const int64_t cg = (P.pos_base / kChunk + c) * kChunk;
+        const int64_t cb = (cg > P.pos_base) ? cg : P.pos_base, ce = (cg + kChunk < P.pos_end) ? cg + kChunk : P.pos_end;
         int64_t lo = 0, hi = P.VV;  // warp-cooperative 32-ary search for the first word with colptr[w+1] > cb
         while (hi - lo > 1) {
             const int64_t step = (hi - lo + 31) >> 5;
@@ -285,6 +292,8 @@ __global__ void __launch_bounds__(256) sstats_fold_kernel(const double* __restri
 }
 
 static int64_t nchunks_for(int64_t nnz) { return (nnz + kChunk - 1) / kChunk; }
+// chunks of the corpus-wide grid that intersect [pos_base, pos_base + nnz)
+static int64_t nchunks_for(int64_t pos_base, int64_t nnz) { return nchunks_for(pos_base % kChunk + nnz); }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
@@ -332,19 +341,19 @@ extern "C" {
 
 int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks)
 {
-    const int64_t nc = nchunks_for(nnz);
+    const int64_t nc = nchunks_for(nnz) + 1;  // + 1: a block that does not start on the chunk grid
     size_t b = align256((size_t)nc * 2 * ld * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t)) + 256;
     if (nblocks > 1) b += align256((size_t)nblocks * V * ld * sizeof(double));
     return (int64_t)b;
 }
 
-int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t D, int64_t V,
-                         int64_t K, int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
-                         const double* exp_elogbeta, const double* ratio_csc, double* sstats, void* workspace,
-                         int64_t workspace_bytes, void* stream)
+static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t D, int64_t V,
+                           int64_t K, int64_t ld, int64_t pos_base, int64_t nnz, int64_t nblocks,
+                           const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
+                           double* sstats, void* workspace, int64_t workspace_bytes, cudaStream_t s)
 {
     TTLDA_REQUIRE(colptr && exp_elogtheta && (exp_elogbeta || ratio_csc) && sstats && workspace, "NULL pointer");
-    TTLDA_REQUIRE(D >= 0 && V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
+    TTLDA_REQUIRE(D >= 0 && V >= 0 && nnz >= 0 && pos_base >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
     TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
     TTLDA_REQUIRE(nblocks >= 1 && nblocks * V < ((int64_t)1 << 31), "bad nblocks");
     if (workspace_bytes < ttlda_sstats_workspace_bytes(nnz, V, ld, nblocks)) {
@@ -352,8 +361,7 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
                   (long long)ttlda_sstats_workspace_bytes(nnz, V, ld, nblocks));
         return TTLDA_EWORKSPACE;
     }
-    cudaStream_t s = (cudaStream_t)stream;
-    const int64_t nc = nchunks_for(nnz);
+    const int64_t nc = nchunks_for(pos_base, nnz);
     char* ws = (char*)workspace;
     double* carry = (double*)ws;
     int32_t* carry_word = (int32_t*)(ws + align256((size_t)nc * 2 * ld * sizeof(double)));
@@ -370,8 +378,8 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
         }
         return TTLDA_OK;
     }
-    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, nnz, nc, exp_elogtheta, exp_elogbeta, ratio_csc, Sb, carry,
-                   carry_word};
+    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, pos_base, pos_base + nnz, nc, exp_elogtheta, exp_elogbeta,
+                   ratio_csc, Sb, carry, carry_word};
     const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
     GroupShape gs = group_shape_for(ld);
     if (const char* ov = getenv("TTLDA_GROUP")) {
@@ -410,6 +418,37 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
         sstats_fold_kernel<<<fg, 256, 0, s>>>(Sb, V, ld, (int)nblocks, sstats);
         TTLDA_LAUNCH_CHECK("sstats_fold");
     }
+    return TTLDA_OK;
+}
+
+int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t D, int64_t V,
+                         int64_t K, int64_t ld, int64_t nnz, int64_t nblocks, const double* exp_elogtheta,
+                         const double* exp_elogbeta, const double* ratio_csc, double* sstats, void* workspace,
+                         int64_t workspace_bytes, void* stream)
+{
+    return sstats_csc_impl(colptr, docidx, ccounts, D, V, K, ld, 0, nnz, nblocks, exp_elogtheta, exp_elogbeta, ratio_csc,
+                           sstats, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_sstats_csc_block_f64(const int64_t* colptr_block, const int32_t* docidx, const int32_t* ccounts, int64_t D,
+                               int64_t V, int64_t K, int64_t ld, int64_t pos_base, int64_t nnz_block,
+                               const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
+                               double* sstats_block, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    return sstats_csc_impl(colptr_block, docidx, ccounts, D, V, K, ld, pos_base, nnz_block, 1, exp_elogtheta,
+                           exp_elogbeta, ratio_csc, sstats_block, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_sstats_fold_f64(const double* sstats_blocks, int64_t nblocks, int64_t V, int64_t ld, double* sstats,
+                          void* stream)
+{
+    TTLDA_REQUIRE(sstats_blocks && sstats, "NULL pointer");
+    TTLDA_REQUIRE(nblocks >= 1 && nblocks < ((int64_t)1 << 31) && V >= 0 && ld >= 1, "bad shape");
+    const int64_t total = V * ld;
+    if (total == 0) return TTLDA_OK;
+    int fg = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
+    sstats_fold_kernel<<<fg, 256, 0, (cudaStream_t)stream>>>(sstats_blocks, V, ld, (int)nblocks, sstats);
+    TTLDA_LAUNCH_CHECK("sstats_fold");
     return TTLDA_OK;
 }
 

@@ -255,13 +255,16 @@ class LDASmoothed:
                      st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
 
-    def _commit_iteration(self, use_ratio: bool = True):
+    def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
-        adopt the E-step's gamma / exp(E[log theta])."""
+        adopt the E-step's gamma / exp(E[log theta]).  have_sstats: st.sstats already holds this rank's statistics
+        (the block-pipelined streaming path)."""
         st, c = self._st, self._st.corpus
         # the statistics use the theta the E-step read — or, in fixed-point mode, the refreshed one it produced
         eT = st.eT[st.cur ^ 1] if self._inner_fixed_point else st.eT[st.cur]
-        if self._sstats_mode == "atomic":
+        if have_sstats:
+            pass
+        elif self._sstats_mode == "atomic":
             nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
         else:
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
@@ -286,16 +289,17 @@ class LDASmoothed:
     # ------------------------------------------------------------------------------------------------------------------
     # streaming entry point: one EM iteration whose corpus arrives from (pinned) host memory
     # ------------------------------------------------------------------------------------------------------------------
-    def em_step_from_host(self, rowptr, colidx, counts, e_num_step: int = 100, chunks: int = 16,
+    def em_step_from_host(self, rowptr, colidx, counts, e_num_step: int = 100, chunks: int = 0,
                           sampling: bool = False) -> float:
         """One EM iteration (lda_model.py:285-316 + the perplexity of the incoming state, :403-409) on a CSR corpus
         that lives in host memory (torch CPU tensors, ideally pinned): rowptr int64[D+1], colidx/counts int32[nnz],
-        same D and V as the fitted corpus.  The upload is pipelined with the E-step: the documents are cut into
-        `chunks` nnz-balanced blocks, block i+1 crosses PCIe on a copy stream while the E-step kernel runs on block i;
-        the CSC mirror is rebuilt on the device once the last block has landed.  Returns the perplexity of the
-        incoming state on this corpus.  This is the per-step path `bench.py` times as `e2e`."""
-        from .corpus import balanced_doc_partition
-
+        same D and V as the fitted corpus.  Everything is pipelined per DOCUMENT BLOCK of the blocked mirror: while
+        block b+1 crosses PCIe on a copy stream, block b is mirrored (ttlda_csr_to_csc_block), E-stepped (leaving c/N
+        per nonzero in mirror order) and accumulated into its partial statistics (ttlda_sstats_csc_block_f64); the
+        partials are folded in block order, then theta refresh and M-step.  Bit-identical to uploading the corpus
+        and running one iteration of `fit`.  Returns the perplexity of the incoming state on this corpus.  This is
+        the per-step path `bench.py` times as `e2e`.  (`chunks` is accepted for compatibility and ignored: the
+        pipeline granularity is the mirror's document block.)"""
         st = self._st
         if st is None:
             raise RuntimeError("fit() first (em_num_step=0 initialises the state without iterating)")
@@ -308,43 +312,70 @@ class LDASmoothed:
             raise ValueError("the streamed corpus must have the fitted number of documents")
         if nnz > c.colidx.numel():
             raise ValueError("the streamed corpus has more nonzeros than the device buffers hold")
+        dev, V, K, ld = st.dev, st.V, st.K, st.ld
+        nb, bd = c.nblocks, c.block_docs
+        rp_np = rowptr.numpy()
+        dlo = [min(b * bd, D) for b in range(nb + 1)]
+        dlo[nb] = D
+        plo = [int(rp_np[d]) for d in dlo]
+        max_blk = max((plo[b + 1] - plo[b] for b in range(nb)), default=0)
+        # buffers that depend on the streamed corpus' nonzero count
+        if c.docidx.numel() < max(nnz, 1):
+            c.docidx = torch.empty(nnz, dtype=torch.int32, device=dev)
+            c.ccounts = torch.empty(nnz, dtype=torch.int32, device=dev)
+            c.csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
+        if st.ratio is not None and st.ratio.numel() < max(nnz, 1):
+            st.ratio = torch.empty(nnz, dtype=torch.float64, device=dev)
+        need = nv.sstats_workspace_bytes(max_blk, V, ld, 1)
+        if st.ws_s.numel() < need:
+            st.ws_s = torch.empty(need, dtype=torch.uint8, device=dev)
+        need = nv.csr_to_csc_workspace_bytes(max_blk, bd, V, 1)
+        if getattr(st, "ws_c", None) is None or st.ws_c.numel() < need:
+            st.ws_c = torch.empty(need, dtype=torch.uint8, device=dev)
+        if nb > 1 and getattr(st, "S_blocks", None) is None:
+            st.S_blocks = torch.empty((nb, V, ld), dtype=torch.float64, device=dev)
+
         compute = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(device=st.dev)
+            self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
         cs.wait_stream(compute)  # the previous iteration may still be reading the corpus buffers
-        rp_np = rowptr.numpy()
-        bounds = balanced_doc_partition(rp_np, max(1, int(chunks)))
         with torch.cuda.stream(cs):
             c.rowptr.copy_(rowptr, non_blocking=True)
         cur, nxt = st.cur, st.cur ^ 1
-        acc = torch.zeros(nv.NPART, dtype=torch.float64, device=st.dev)
-        it_acc = torch.zeros(2, dtype=torch.int64, device=st.dev)
-        for i in range(len(bounds) - 1):
-            d0, d1 = int(bounds[i]), int(bounds[i + 1])
+        acc = torch.zeros(nv.NPART, dtype=torch.float64, device=dev)
+        it_acc = torch.zeros(2, dtype=torch.int64, device=dev)
+        use_ratio = st.ratio is not None
+        for b in range(nb):
+            d0, d1, s, e = dlo[b], dlo[b + 1], plo[b], plo[b + 1]
             if d1 <= d0:
                 continue
-            s, e = int(rp_np[d0]), int(rp_np[d1])
             with torch.cuda.stream(cs):
                 c.colidx[s:e].copy_(colidx[s:e], non_blocking=True)
                 c.counts[s:e].copy_(counts[s:e], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
             compute.wait_event(ev)
-            nv.estep(c.rowptr[d0:d1 + 1], c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(),
+            colptr_b = c.colptr[b * V:b * V + V + 1]
+            nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, colptr_b, c.docidx,
+                                c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
+            nv.estep(c.rowptr[d0:d1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
                      st.eT[cur][d0:d1], st.eB, st.gamma[cur][d0:d1], st.gamma[nxt][d0:d1], None, e_num_step, 1e-05,
-                     st.iters, st.part[0], st.ws)
+                     st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
             acc += st.part[0]
             it_acc += st.iters
+            nv.sstats_csc_block(colptr_b, c.docidx, c.ccounts, V, K, s, e - s, st.eT[cur], st.eB,
+                                st.S_blocks[b] if nb > 1 else st.sstats, st.ws_s, st.ratio)
         c.nnz = nnz
-        c.build_csc(c.nblocks, c.block_docs, with_map=False)
+        if nb > 1:
+            nv.sstats_fold(st.S_blocks, st.sstats)
         st.part[0].copy_(acc)
         st.iters.copy_(it_acc)
         self.inner_iterations, capped = self._collect(tok_row=0)
         perplexity = self._perplexity_from_terms(sampling)
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
-        self._commit_iteration(use_ratio=False)  # no csr2csc map existed while the E-step ran: recompute c/N
+        self._commit_iteration(have_sstats=True)
         return perplexity
 
     def _collect(self, tok_row: int):
