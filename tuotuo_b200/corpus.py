@@ -16,9 +16,11 @@ from . import _native as nv
 class DeviceCorpus:
     """rowptr int64[D+1], colidx int32[nnz] (ascending per row), counts int32[nnz] and the CSC mirror, on one device."""
 
-    L2_WINDOW_BYTES = 96 << 20   # exp(E[log theta]) rows one document block may occupy (126 MB L2 on B200;
-                                 # measured optimum at cfg3: 8-12 blocks of 66-100 MB, DESIGN.md §5)
-    MAX_BLOCK_BYTES = 2 << 30    # cap on the per-block statistics buffer nblocks * V * ld * 8
+    L2_WINDOW_BYTES = 50 << 20   # exp(E[log theta]) rows one document block may occupy: well under half of the 126 MB
+                                 # L2 (two 63 MB partitions).  Measured at cfg3 with ticket-ordered chunks: statistics
+                                 # pass 11.0 ms at 8 blocks (100 MB), 9.1 ms at 12-24 blocks (67-33 MB), DESIGN.md §5
+    MAX_BLOCK_BYTES = 12 << 30   # cap on the per-block statistics buffer nblocks * V * ld * 8 (cfg4: 23 x 411 MB; its
+                                 # write + fold costs ~3 ms and saves ~23 ms of HBM gathers)
 
     def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = False):
         assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and counts.dtype == torch.int32

@@ -44,6 +44,7 @@ struct SStatsParams {
     double* S;           // [VV][ld] per-(block, word) statistics (== the final [V][ld] table when nblocks == 1)
     double* carry;       // [nchunks][2][ld]  head / tail partials of words cut by a chunk boundary
     int32_t* carry_word; // [nchunks][2]      virtual word id of each carry slot, -1 = unused
+    unsigned long long* ticket;  // next chunk to hand out (zeroed before the launch)
 };
 
 // USE_RATIO: the E-step left c/N per posting (ttlda_estep_f64 ratio_csc): the pass is then a pure gather-accumulate
@@ -59,13 +60,19 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
 
     const int lane = threadIdx.x & 31;
     const int g = lane % G, r = lane / G;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld;
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
     const uint64_t pol = l2_evict_first_policy();
 
-    for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
+    // Chunks are handed out in mirror order through a global ticket counter, so that the warps resident at any moment
+    // work on ~one narrow range of positions => on ONE document block's exp(E[log theta]) window, which then stays in
+    // L2 until the whole block is done (a static chunk -> warp map lets waves of CTAs and fast warps drift across
+    // blocks and re-read every window several times: 73 GB of DRAM traffic per pass at cfg3, profiles/r01h).
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(P.ticket, 1ull);
+        const int64_t c = (int64_t)__shfl_sync(0xffffffffu, ticket, 0);
+        if (c >= P.nchunks) break;
         // chunks sit on the corpus-wide grid of kChunk positions (so a block processed on its own cuts its words exactly
         // where the one-call pass over the whole mirror does => identical bits)
         const int64_t cg = (P.pos_base / kChunk + c) * kChunk;
@@ -172,8 +179,6 @@ __global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __gri
 
     const int lane = threadIdx.x & 31;
     const int g = lane % G, r = lane / G;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int ld = (int)P.ld;
     const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
     const uint64_t pol = l2_evict_first_policy();
@@ -182,7 +187,15 @@ __global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __gri
     pipe.init(wbase, ld, lane);
     double* wbuf = reinterpret_cast<double*>(wbase);  // the segment epilogue's transpose buffer aliases the drained stages
 
-    for (int64_t c = warp0; c < P.nchunks; c += nwarps) {
+    // Chunks are handed out in mirror order through a global ticket counter, so that the warps resident at any moment
+    // work on ~one narrow range of positions => on ONE document block's exp(E[log theta]) window, which then stays in
+    // L2 until the whole block is done (a static chunk -> warp map lets waves of CTAs and fast warps drift across
+    // blocks and re-read every window several times: 73 GB of DRAM traffic per pass at cfg3, profiles/r01h).
+    for (;;) {
+        unsigned long long ticket = 0;
+        if (lane == 0) ticket = atomicAdd(P.ticket, 1ull);
+        const int64_t c = (int64_t)__shfl_sync(0xffffffffu, ticket, 0);
+        if (c >= P.nchunks) break;
         // chunks sit on the corpus-wide grid of kChunk positions (so a block processed on its own cuts its words exactly
         // where the one-call pass over the whole mirror does => identical bits)
         const int64_t cg = (P.pos_base / kChunk + c) * kChunk;
@@ -342,8 +355,9 @@ extern "C" {
 int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t nblocks)
 {
     const int64_t nc = nchunks_for(nnz) + 1;  // + 1: a block that does not start on the chunk grid
-    size_t b = align256((size_t)nc * 2 * ld * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t)) + 256;
-    if (nblocks > 1) b += align256((size_t)nblocks * V * ld * sizeof(double));
+    // [256: ticket][carry][carry_word][per-block partials, nblocks > 1 only — always the last bytes]
+    size_t b = 256 + align256((size_t)nc * 2 * ld * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t));
+    if (nblocks > 1) b += (size_t)nblocks * V * ld * sizeof(double);
     return (int64_t)b;
 }
 
@@ -363,10 +377,15 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
     }
     const int64_t nc = nchunks_for(pos_base, nnz);
     char* ws = (char*)workspace;
+    unsigned long long* ticket = (unsigned long long*)ws;
+    ws += 256;
+    const int64_t nc_cap = nchunks_for(nnz) + 1;  // the layout ttlda_sstats_workspace_bytes sized (nc <= nc_cap)
     double* carry = (double*)ws;
-    int32_t* carry_word = (int32_t*)(ws + align256((size_t)nc * 2 * ld * sizeof(double)));
+    int32_t* carry_word = (int32_t*)(ws + align256((size_t)nc_cap * 2 * ld * sizeof(double)));
+    // the per-block partials are the TAIL of the workspace (callers of the block entry points may use that region as
+    // their [nblocks][V][ld] buffer: it is not touched by single-block calls)
     double* Sb = (nblocks > 1)
-                     ? (double*)((char*)carry_word + align256((size_t)nc * 2 * sizeof(int32_t)))
+                     ? (double*)((char*)carry_word + align256((size_t)nc_cap * 2 * sizeof(int32_t)))
                      : sstats;
     const int64_t VV = nblocks * V;
     cudaError_t e = cudaMemsetAsync(Sb, 0, (size_t)VV * ld * sizeof(double), s);  // words with no postings
@@ -379,7 +398,9 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
         return TTLDA_OK;
     }
     SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, pos_base, pos_base + nnz, nc, exp_elogtheta, exp_elogbeta,
-                   ratio_csc, Sb, carry, carry_word};
+                   ratio_csc, Sb, carry, carry_word, ticket};
+    e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return cuda_fail(e, "memset ticket");
     const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
     GroupShape gs = group_shape_for(ld);
     if (const char* ov = getenv("TTLDA_GROUP")) {

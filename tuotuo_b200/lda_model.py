@@ -326,14 +326,16 @@ class LDASmoothed:
             c.csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
         if st.ratio is not None and st.ratio.numel() < max(nnz, 1):
             st.ratio = torch.empty(nnz, dtype=torch.float64, device=dev)
-        need = nv.sstats_workspace_bytes(max_blk, V, ld, 1)
-        if st.ws_s.numel() < need:
-            st.ws_s = torch.empty(need, dtype=torch.uint8, device=dev)
+        # statistics workspace: head for one block's pass; the per-block partials live where the one-call pass keeps
+        # them, in the tail of the same workspace
+        tail = nb * V * ld * 8 if nb > 1 else 0
+        if st.ws_s.numel() < nv.sstats_workspace_bytes(max_blk, V, ld, 1) + tail or (st.ws_s.numel() - tail) % 8:
+            st.ws_s = torch.empty(nv.sstats_workspace_bytes(max(nnz, c.nnz), V, ld, nb), dtype=torch.uint8, device=dev)
+        if nb > 1:
+            st.S_blocks = st.ws_s[st.ws_s.numel() - tail:].view(torch.float64).view(nb, V, ld)
         need = nv.csr_to_csc_workspace_bytes(max_blk, bd, V, 1)
         if getattr(st, "ws_c", None) is None or st.ws_c.numel() < need:
             st.ws_c = torch.empty(need, dtype=torch.uint8, device=dev)
-        if nb > 1 and getattr(st, "S_blocks", None) is None:
-            st.S_blocks = torch.empty((nb, V, ld), dtype=torch.float64, device=dev)
 
         compute = torch.cuda.current_stream()
         if getattr(self, "_copy_stream", None) is None:
