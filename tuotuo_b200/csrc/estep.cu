@@ -162,6 +162,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
             nx_c = ld_stream_s32(P.counts + b + lane, pol);
             if (ESTEP && P.ratio_csc) nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + b + lane, pol);
         }
+        KSlice<G, E> rowA;  // sub-batch 0 of the coming batch (carried across batches when PREFETCH)
+        if (PREFETCH && b < e) rowA.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, nx_w, r) * P.ld, g, last_ok);
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
             const int my_w = nx_w, my_c = nx_c, my_pos = nx_pos;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                     nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + n0 + 32 + lane, pol);
             }
             double my_p = 1.;
-            walk_rows<G, E, PREFETCH>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
+            auto body = [&](int s, const KSlice<G, E>& row) {
                 const int i = s * R + r;                          // nonzero handled by this group in this sub-batch
                 const int c = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt: the group idles harmlessly
                 const double p = group_sum<G>(t.dot(row));
@@ -185,7 +187,9 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == s) my_p = pv;
-            });
+            };
+            if (PREFETCH) walk_rows_carried<G, E>(P.eB, P.ld, my_w, cnt, nx_w, n0 + 32 < e, rowA, g, r, last_ok, body);
+            else walk_rows<G, E, false>(P.eB, P.ld, my_w, cnt, g, r, last_ok, body);
             if (lane < cnt) {  // one log per nonzero
                 tok_acc += (double)my_c * log(my_p);
                 cnt_acc += (double)my_c;

@@ -117,6 +117,8 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                 if (USE_RATIO) nx_r = ld_stream_f64(P.ratio + pos + lane, pol);
                 else nx_c = ld_stream_s32(P.ccounts + pos + lane, pol);
             }
+            KSlice<G, E> rowA;  // sub-batch 0 of the coming batch (carried across batches when PREFETCH)
+            if (PREFETCH) rowA.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, nx_d, r) * P.ld, g, last_ok);
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
                 const int my_d = nx_d, my_c = nx_c;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                     if (USE_RATIO) nx_r = ld_stream_f64(P.ratio + n0 + 32 + lane, pol);
                     else nx_c = ld_stream_s32(P.ccounts + n0 + 32 + lane, pol);
                 }
-                walk_rows<G, E, PREFETCH>(P.eT, P.ld, my_d, cnt, g, r, last_ok, [&](int s, const KSlice<G, E>& row) {
+                auto body = [&](int s, const KSlice<G, E>& row) {
                     if (USE_RATIO) {
                         acc.axpy(__shfl_sync(0xffffffffu, my_r, s * R + r), row);  // 0 past the end of the segment
                     } else {
@@ -137,7 +139,11 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                         const double p = group_sum<G>(b.dot(row));
                         acc.axpy(fast_div_pos((double)cc, p + 1e-100), row);  // lda_model.py:242,262
                     }
-                });
+                };
+                if (PREFETCH)
+                    walk_rows_carried<G, E>(P.eT, P.ld, my_d, cnt, nx_d, n0 + 32 < se, rowA, g, r, last_ok, body);
+                else
+                    walk_rows<G, E, false>(P.eT, P.ld, my_d, cnt, g, r, last_ok, body);
             }
             // group partials -> one K-vector, written with coalesced stores
             acc.to_smem(wbuf + r * LDP, g);

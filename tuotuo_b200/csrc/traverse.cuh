@@ -98,6 +98,36 @@ __device__ __forceinline__ void walk_rows(const double* __restrict__ table, int6
     }
 }
 
+// The same walk with the row pipeline carried ACROSS 32-row batches: A arrives holding sub-batch 0 of this batch
+// (loaded by the caller or by the previous call) and leaves holding sub-batch 0 of the next batch (rows `next_idx`,
+// fetched by the caller one batch ahead), whose loads are issued as soon as A's last use in this batch is over.
+// Without this every batch starts with one fully exposed load latency — 27 % of the E-step's stall samples sat on
+// that first use (profiles/r01h source view).
+template <int G, int E, class Body>
+__device__ __forceinline__ void walk_rows_carried(const double* __restrict__ table, int64_t ld64, int my_idx, int cnt,
+                                                  int next_idx, bool has_next, KSlice<G, E>& A, int g, int r,
+                                                  bool last_ok, Body&& body)
+{
+    constexpr int R = 32 / G;
+    const int nsub = (cnt + R - 1) / R;
+    KSlice<G, E> B;
+    int s = 0;
+    while (true) {
+        if (s + 1 < nsub) B.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+        body(s, A);
+        if (++s >= nsub) {  // odd number of sub-batches (a partial batch): A is free only now
+            if (has_next) A.load(table + (int64_t)__shfl_sync(0xffffffffu, next_idx, r) * ld64, g, last_ok);
+            break;
+        }
+        if (s + 1 < nsub)
+            A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+        else if (has_next)
+            A.load(table + (int64_t)__shfl_sync(0xffffffffu, next_idx, r) * ld64, g, last_ok);
+        body(s, B);
+        if (++s >= nsub) break;
+    }
+}
+
 // sum over the G lanes of a group (result in every lane of the group)
 template <int G>
 __device__ __forceinline__ double group_sum(double p)
