@@ -87,6 +87,11 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
                      int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Unsigned 8- or 16-bit items -> int32 (src_bytes_per_item = 1 | 2).  Lets a corpus cross PCIe in a compact form
+ * (uint16 word ids when V <= 65536, uint8/uint16 counts: 3 instead of 8 bytes per nonzero) and be widened into the
+ * colidx / counts arrays on the device. */
+int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, int64_t n, void* stream);
+
 /* One document block of a document-blocked mirror, built on its own (streaming ingestion: block b can be mirrored,
  * E-stepped and accumulated while block b+1 is still crossing PCIe).  The block holds documents
  * [doc_base, doc_base + D_block) whose entries occupy positions [pos_base, pos_base + nnz_block) of the corpus-wide

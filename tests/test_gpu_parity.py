@@ -488,6 +488,41 @@ def test_em_step_from_host_equals_resident_iteration(monkeypatch, blocks, handof
     assert m.inner_iterations == 2 * 900
 
 
+@pytest.mark.parametrize("ci_dtype,ct_dtype", [(np.uint16, np.uint8), (np.int32, np.uint16), (np.uint16, np.int32)])
+def test_em_step_from_host_compact_formats(monkeypatch, ci_dtype, ct_dtype):
+    """16-bit word ids / 8- or 16-bit counts in host memory are widened on the device (ttlda_widen_i32): same bits
+    as the int32 form.  Word ids above 32767 and counts above 127 exercise the unsigned interpretation."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", "3")
+    V = 40000
+    rp, ci, ct = numpy_corpus(67, 400, V, 10, 120, ragged=True)
+    ci = (ci.astype(np.int64) * 7 % V).astype(np.int32)  # spread ids over [0, V), then restore the per-row order
+    for d in range(len(rp) - 1):
+        seg = slice(rp[d], rp[d + 1])
+        u, first = np.unique(ci[seg], return_index=True)
+        assert len(u) == rp[d + 1] - rp[d]
+        ct[seg] = ct[seg][first]
+        ci[seg] = u
+    ct = ct.copy()
+    ct[::5] = 200  # > 127
+    assert ci.max() > 32767
+    res = []
+    for a_ci, a_ct in ((ci, ct), (ci.astype(ci_dtype), ct.astype(ct_dtype))):
+        m = LDASmoothed(24, verbose=False)
+        m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=0, update_hyper_parms=False)
+        h = [torch.as_tensor(rp).pin_memory()]
+        for a in (a_ci, a_ct):  # torch has no from_numpy for uint16 everywhere: hand over the bit pattern
+            t = torch.as_tensor(a.view(np.int16) if a.dtype == np.uint16 else a)
+            h.append(t.pin_memory())
+        ps = [m.em_step_from_host(*h) for _ in range(2)]
+        res.append((ps, m._gamma_.copy(), m._lambda_.copy()))
+    assert res[0][0] == res[1][0]
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+
+
 def test_block_entry_points_equal_one_call_forms(nv, dev):
     """ttlda_csr_to_csc_block / ttlda_sstats_csc_block_f64 + ttlda_sstats_fold_f64 over every block reproduce
     ttlda_csr_to_csc / ttlda_sstats_csc_f64 with nblocks > 1 exactly (blocks that do not start on the chunk grid,

@@ -63,9 +63,9 @@ void run(const char* name, const double* table, const int* idx, const int* cnts,
            (double)n * ld * 8 / ms / 1e6, cudaGetErrorString(cudaGetLastError()));
 }
 
-int main()
+int main(int argc, char** argv)
 {
-    const int ld = 100;
+    const int ld = argc > 1 ? atoi(argv[1]) : 100;
     const long n = 192L * 148 * 16 * 4 * 22;  // ~40M rows
     double* out; cudaMalloc(&out, 8);
     for (int zipf = 0; zipf < 2; ++zipf) {

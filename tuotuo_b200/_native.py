@@ -36,6 +36,7 @@ SIGNATURES = {
                                         _i64, _ptr]),
     "ttlda_csr_to_csc_block": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
                                               _ptr, _i64, _ptr]),
+    "ttlda_widen_i32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr]),
     "ttlda_reduce_workspace_bytes": (_i64, []),
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
@@ -74,7 +75,7 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 # hand-written kernels launched by each entry point (CUB sort/RLE passes and memsets are not counted)
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
-    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2,
+    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1,
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4,
@@ -198,6 +199,13 @@ def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, d
     _call("ttlda_csr_to_csc", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), int(D), int(V), int(nnz),
           int(nblocks), int(block_docs), _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), _p(csr2csc, torch.int32),
           _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def widen_i32(src, dst):
+    """uint8 / int16-or-uint16 bit patterns (unsigned) -> int32, elementwise."""
+    if src.element_size() not in (1, 2) or src.numel() != dst.numel():
+        raise TTLDAError("widen_i32: source must hold 1- or 2-byte items, one per destination item")
+    _call("ttlda_widen_i32", _p(src), src.element_size(), _p(dst, i32), src.numel(), _stream())
 
 
 def csr_to_csc_block(rowptr_block, colidx, counts, V, doc_base, pos_base, nnz_block, colptr_block, docidx, ccounts, ws,

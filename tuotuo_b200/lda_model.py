@@ -292,7 +292,8 @@ class LDASmoothed:
     def em_step_from_host(self, rowptr, colidx, counts, e_num_step: int = 100, chunks: int = 0,
                           sampling: bool = False) -> float:
         """One EM iteration (lda_model.py:285-316 + the perplexity of the incoming state, :403-409) on a CSR corpus
-        that lives in host memory (torch CPU tensors, ideally pinned): rowptr int64[D+1], colidx/counts int32[nnz],
+        that lives in host memory (torch CPU tensors, ideally pinned): rowptr int64[D+1], colidx/counts int32[nnz]
+        — or compact: colidx uint16/int16 bit patterns when V <= 65536, counts uint8 or uint16, widened on the device —
         same D and V as the fitted corpus.  Everything is pipelined per DOCUMENT BLOCK of the blocked mirror: while
         block b+1 crosses PCIe on a copy stream, block b is mirrored (ttlda_csr_to_csc_block), E-stepped (leaving c/N
         per nonzero in mirror order) and accumulated into its partial statistics (ttlda_sstats_csc_block_f64); the
@@ -344,6 +345,23 @@ class LDASmoothed:
         cs.wait_stream(compute)  # the previous iteration may still be reading the corpus buffers
         with torch.cuda.stream(cs):
             c.rowptr.copy_(rowptr, non_blocking=True)
+        # compact host formats: 2-byte word ids (V <= 65536) and 1- or 2-byte counts, all unsigned, are staged as they
+        # are and widened into the int32 arrays on the device (3 instead of 8 bytes per nonzero over PCIe)
+        def staged(host, name):
+            if host.dtype == torch.int32:
+                return host, None
+            if host.element_size() not in (1, 2) or host.dtype.is_floating_point:
+                raise TypeError(f"{name}: int32, or an unsigned 8/16-bit integer type, expected; got {host.dtype}")
+            host = host.view(torch.uint8 if host.element_size() == 1 else torch.int16)
+            buf = getattr(st, "stage_" + name, None)
+            if buf is None or buf.dtype != host.dtype or buf.numel() < max(nnz, 1):
+                buf = torch.empty(max(nnz, 1), dtype=host.dtype, device=dev)
+                setattr(st, "stage_" + name, buf)
+            return host, buf
+        if colidx.element_size() == 2 and V > 65536:
+            raise ValueError("16-bit word ids need V <= 65536")
+        colidx, stage_ci = staged(colidx, "colidx")
+        counts, stage_ct = staged(counts, "counts")
         cur, nxt = st.cur, st.cur ^ 1
         acc = torch.zeros(nv.NPART, dtype=torch.float64, device=dev)
         it_acc = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -353,11 +371,15 @@ class LDASmoothed:
             if d1 <= d0:
                 continue
             with torch.cuda.stream(cs):
-                c.colidx[s:e].copy_(colidx[s:e], non_blocking=True)
-                c.counts[s:e].copy_(counts[s:e], non_blocking=True)
+                (c.colidx if stage_ci is None else stage_ci)[s:e].copy_(colidx[s:e], non_blocking=True)
+                (c.counts if stage_ct is None else stage_ct)[s:e].copy_(counts[s:e], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(cs)
             compute.wait_event(ev)
+            if stage_ci is not None:
+                nv.widen_i32(stage_ci[s:e], c.colidx[s:e])
+            if stage_ct is not None:
+                nv.widen_i32(stage_ct[s:e], c.counts[s:e])
             colptr_b = c.colptr[b * V:b * V + V + 1]
             nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, colptr_b, c.docidx,
                                 c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
