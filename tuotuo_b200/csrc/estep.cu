@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
             if (ESTEP && P.ratio_csc) nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + b + lane, pol);
         }
         KSlice<G, E> rowA;  // sub-batch 0 of the coming batch (carried across batches when PREFETCH)
-        if (PREFETCH && b < e) rowA.load(P.eB + (int64_t)__shfl_sync(0xffffffffu, nx_w, r) * P.ld, g, last_ok);
+        if (PREFETCH && b < e) rowA.load_at(row_at(P.eB + 2 * g, __shfl_sync(0xffffffffu, nx_w, r), ld), last_ok);
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
             const int my_w = nx_w, my_c = nx_c, my_pos = nx_pos;
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == s) my_p = pv;
             };
-            if (PREFETCH) walk_rows_carried<G, E>(P.eB, P.ld, my_w, cnt, nx_w, n0 + 32 < e, rowA, g, r, last_ok, body);
-            else walk_rows<G, E, false>(P.eB, P.ld, my_w, cnt, g, r, last_ok, body);
+            if (PREFETCH) walk_rows_carried<G, E>(P.eB, ld, my_w, cnt, nx_w, n0 + 32 < e, rowA, g, r, last_ok, body);
+            else walk_rows<G, E, false>(P.eB, ld, my_w, cnt, g, r, last_ok, body);
             if (lane < cnt) {  // one log per nonzero
                 tok_acc += (double)my_c * log(my_p);
                 cnt_acc += (double)my_c;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(kFpThreads) doc_fixed_point_kernel(const Fixed
                     my_c = ld_stream_s32(P.counts + n0 + lane, pol);
                 }
                 double my_p = 1.;
-                walk_rows<G, E, PF>(P.eB, P.ld, my_w, cnt, g, r, last_ok, [&](int sb, const KSlice<G, E>& row) {
+                walk_rows<G, E, PF>(P.eB, (int)P.ld, my_w, cnt, g, r, last_ok, [&](int sb, const KSlice<G, E>& row) {
                     const int c = __shfl_sync(0xffffffffu, my_c, sb * R + r);
                     const double p = group_sum<G>(t.dot(row));
                     acc.axpy(fast_div_pos((double)c, p + 1e-100), row);  // lda_model.py:242,248

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                 else nx_c = ld_stream_s32(P.ccounts + pos + lane, pol);
             }
             KSlice<G, E> rowA;  // sub-batch 0 of the coming batch (carried across batches when PREFETCH)
-            if (PREFETCH) rowA.load(P.eT + (int64_t)__shfl_sync(0xffffffffu, nx_d, r) * P.ld, g, last_ok);
+            if (PREFETCH) rowA.load_at(row_at(P.eT + 2 * g, __shfl_sync(0xffffffffu, nx_d, r), ld), last_ok);
             for (int64_t n0 = pos; n0 < se; n0 += 32) {
                 const int cnt = (int)((se - n0 < 32) ? (se - n0) : 32);
                 const int my_d = nx_d, my_c = nx_c;
@@ -141,9 +141,9 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                     }
                 };
                 if (PREFETCH)
-                    walk_rows_carried<G, E>(P.eT, P.ld, my_d, cnt, nx_d, n0 + 32 < se, rowA, g, r, last_ok, body);
+                    walk_rows_carried<G, E>(P.eT, ld, my_d, cnt, nx_d, n0 + 32 < se, rowA, g, r, last_ok, body);
                 else
-                    walk_rows<G, E, false>(P.eT, P.ld, my_d, cnt, g, r, last_ok, body);
+                    walk_rows<G, E, false>(P.eT, ld, my_d, cnt, g, r, last_ok, body);
             }
             // group partials -> one K-vector, written with coalesced stores
             acc.to_smem(wbuf + r * LDP, g);

@@ -29,6 +29,13 @@ struct KSlice {
         for (int j = 0; j < E - 1; ++j) v[j] = ldg2(row + 2 * (g + G * j));
         v[E - 1] = last_ok ? ldg2(row + 2 * (g + G * (E - 1))) : make_double2(0., 0.);
     }
+    // the same with the lane's offset (2 g doubles) already folded into the pointer: offsets are compile-time constants
+    __device__ __forceinline__ void load_at(const double* __restrict__ rowg, bool last_ok)
+    {
+#pragma unroll
+        for (int j = 0; j < E - 1; ++j) v[j] = ldg2(rowg + 2 * G * j);
+        v[E - 1] = last_ok ? ldg2(rowg + 2 * G * (E - 1)) : make_double2(0., 0.);
+    }
     static __device__ __forceinline__ bool last_slice_ok(int g, int ld) { return 2 * (g + G * (E - 1)) < ld; }
     __device__ __forceinline__ void zero()
     {
@@ -67,32 +74,40 @@ struct KSlice {
     }
 };
 
+// row `idx` of a table whose lane offset is already folded into `tg`: one unsigned 32 x 32 -> 64 multiply-add
+__device__ __forceinline__ const double* row_at(const double* tg, int idx, int ld32)
+{
+    return tg + (size_t)(uint32_t)idx * (uint32_t)ld32;
+}
+
+// (ld32: the leading dimension as a 32-bit int, so that row * ld is ONE IMAD.WIDE instead of a 64 x 64 multiply)
 // Software-pipelined walk over the `cnt` (<= 32) rows whose indices the lanes hold in `my_idx` (lane i holds row
 // i): sub-batch s gives group r the row of lane s*R + r.  Two register buffers alternate (explicit ping-pong: no
 // register copies), the loads of sub-batch s+1 are issued before sub-batch s is consumed.
 // body(s, slice) is called once per sub-batch, warp-uniformly.
 template <int G, int E, bool PREFETCH, class Body>
-__device__ __forceinline__ void walk_rows(const double* __restrict__ table, int64_t ld64, int my_idx, int cnt, int g,
+__device__ __forceinline__ void walk_rows(const double* __restrict__ table, int ld32, int my_idx, int cnt, int g,
                                           int r, bool last_ok, Body&& body)
 {
     constexpr int R = 32 / G;
     const int nsub = (cnt + R - 1) / R;
+    const double* tg = table + 2 * g;
     KSlice<G, E> A;
     if (PREFETCH) {
         KSlice<G, E> B;
-        A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, r) * ld64, g, last_ok);
+        A.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, r), ld32), last_ok);
         int s = 0;
         while (true) {
-            if (s + 1 < nsub) B.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+            if (s + 1 < nsub) B.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r), ld32), last_ok);
             body(s, A);
             if (++s >= nsub) break;
-            if (s + 1 < nsub) A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+            if (s + 1 < nsub) A.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r), ld32), last_ok);
             body(s, B);
             if (++s >= nsub) break;
         }
     } else {
         for (int s = 0; s < nsub; ++s) {
-            A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, s * R + r) * ld64, g, last_ok);
+            A.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, s * R + r), ld32), last_ok);
             body(s, A);
         }
     }
@@ -104,25 +119,26 @@ __device__ __forceinline__ void walk_rows(const double* __restrict__ table, int6
 // Without this every batch starts with one fully exposed load latency — 27 % of the E-step's stall samples sat on
 // that first use (profiles/r01h source view).
 template <int G, int E, class Body>
-__device__ __forceinline__ void walk_rows_carried(const double* __restrict__ table, int64_t ld64, int my_idx, int cnt,
+__device__ __forceinline__ void walk_rows_carried(const double* __restrict__ table, int ld32, int my_idx, int cnt,
                                                   int next_idx, bool has_next, KSlice<G, E>& A, int g, int r,
                                                   bool last_ok, Body&& body)
 {
     constexpr int R = 32 / G;
     const int nsub = (cnt + R - 1) / R;
+    const double* tg = table + 2 * g;
     KSlice<G, E> B;
     int s = 0;
     while (true) {
-        if (s + 1 < nsub) B.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+        if (s + 1 < nsub) B.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r), ld32), last_ok);
         body(s, A);
         if (++s >= nsub) {  // odd number of sub-batches (a partial batch): A is free only now
-            if (has_next) A.load(table + (int64_t)__shfl_sync(0xffffffffu, next_idx, r) * ld64, g, last_ok);
+            if (has_next) A.load_at(row_at(tg, __shfl_sync(0xffffffffu, next_idx, r), ld32), last_ok);
             break;
         }
         if (s + 1 < nsub)
-            A.load(table + (int64_t)__shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r) * ld64, g, last_ok);
+            A.load_at(row_at(tg, __shfl_sync(0xffffffffu, my_idx, (s + 1) * R + r), ld32), last_ok);
         else if (has_next)
-            A.load(table + (int64_t)__shfl_sync(0xffffffffu, next_idx, r) * ld64, g, last_ok);
+            A.load_at(row_at(tg, __shfl_sync(0xffffffffu, next_idx, r), ld32), last_ok);
         body(s, B);
         if (++s >= nsub) break;
     }
