@@ -91,11 +91,25 @@ __device__ __forceinline__ double psi_as103(double x)
 //     is folded into ONE division: sum_i 1/(x+i) = q/p with p = prod_i (x+i), q accumulated by FMA — same value to
 //     ~1e-16 relative (parity needs 1e-9), ~5x fewer instructions;
 //   * lgamma(x) = Stirling(x_shifted) - log(p), series through x^-13 (|err| < 6e-14 absolute for x_shifted >= 6).
-__device__ __forceinline__ void psi_lgamma_as103(double x, double& psi_out, double& lgam_out)
+//   * callers that only need SUMS of lgamma (the ELBO prior terms) take the Stirling part and the shift product p
+//     separately (psi_lgamma_as103_split): sum_k log(p_k) = log(prod_k p_k) costs one log per lane instead of one
+//     per element; the two remaining quotients use the reciprocal approximation + Newton (fast_rcp_pos, ~2 ulp).
+__device__ __forceinline__ double fast_rcp_pos(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-x, y, 2.);
+    y = y * fma(-x, y, 2.);
+    return y;
+}
+
+// psi_out = AS-103 digamma(x);  lgamma(x) = lgam_stirling - log(p_out)   (p_out = 1 when no shift was needed)
+__device__ __forceinline__ void psi_lgamma_as103_split(double x, double& psi_out, double& lgam_stirling, double& p_out)
 {
     if (x <= 1e-6) {  // cutils.pyx:76-78
         psi_out = -0.577215664901532860606512090082402431 - 1. / x;
-        lgam_out = lgamma(x);
+        lgam_stirling = lgamma(x);
+        p_out = 1.;
         return;
     }
     double p = 1., q = 0.;
@@ -104,16 +118,24 @@ __device__ __forceinline__ void psi_lgamma_as103(double x, double& psi_out, doub
         p *= x;
         x += 1.;
     }
-    const double r = 1. / x, lx = log(x), r2 = r * r;  // cutils.pyx:89-92
+    const double r = fast_rcp_pos(x), lx = log(x), r2 = r * r;  // cutils.pyx:89-92
     double res = lx - .5 * r;
     res -= r2 * ((1. / 12.) - r2 * ((1. / 120.) - r2 * (1. / 252.)));
-    psi_out = res - q / p;
+    psi_out = res - q * fast_rcp_pos(p);
     const double series =
         r * ((1. / 12.) -
              r2 * ((1. / 360.) -
                    r2 * ((1. / 1260.) -
                          r2 * ((1. / 1680.) - r2 * ((1. / 1188.) - r2 * ((691. / 360360.) - r2 * (1. / 156.)))))));
-    lgam_out = (x - .5) * lx - x + 0.91893853320467274178 + series - log(p);
+    lgam_stirling = (x - .5) * lx - x + 0.91893853320467274178 + series;
+    p_out = p;
+}
+
+__device__ __forceinline__ void psi_lgamma_as103(double x, double& psi_out, double& lgam_out)
+{
+    double st, p;
+    psi_lgamma_as103_split(x, psi_out, st, p);
+    lgam_out = (p == 1.) ? st : st - log(p);
 }
 
 // Exact digamma for x > 0 (recurrence to x >= 10, then the asymptotic series through x^-14; |err| ~ 1e-16
