@@ -7,6 +7,7 @@
 // HBM-bound elementwise/row kernels: rows are read once with coalesced accesses, reductions are warp shuffles
 // (rows <= 2048 columns: one warp per row) or a CTA per row (long rows, e.g. a (K,V) matrix).
 #include "ttlda_common.cuh"
+#include "traverse.cuh"
 
 namespace ttlda {
 
@@ -78,14 +79,20 @@ __global__ void dirichlet_1d_kernel(double* __restrict__ doc_topic, double prior
 }
 
 // ---- theta refresh: eT = exp(DE(gamma)), theta-prior term ------------------------------------------------------
-// One warp per document; lane l owns topics l, l+32, ...  Partial record per CTA -> fixed-order final reduction.
+// LPD lanes per document (32 / LPD documents per warp); lane l of a group owns topics l, l + LPD, ...  The digamma /
+// log-gamma evaluations are warp-wide instructions, so what counts is evaluations per document:
+// (ceil(K / LPD) + 1 for the row sum) * LPD / 32 — K = 100: 5 with a full warp, 3.5 with 8 lanes; K = 20: 2 vs 0.75
+// with 4 lanes.  Partial record per CTA -> fixed-order final reduction.
+template <int LPD>
 __global__ void __launch_bounds__(256) theta_refresh_kernel(const double* __restrict__ gamma, int64_t D, int K,
                                                             int64_t ld, const double* __restrict__ alpha_vec,
                                                             double alpha_sum, double* __restrict__ eT,
                                                             double* __restrict__ records)
 {
+    constexpr int DPW = 32 / LPD;  // documents per warp
     __shared__ double sm[32];
     const int lane = threadIdx.x & 31;
+    const int l = lane % LPD, grp = lane / LPD;
     const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     // per-warp constants: sum_k lgamma(alpha_k), lgamma(sum(alpha))
@@ -94,32 +101,41 @@ __global__ void __launch_bounds__(256) theta_refresh_kernel(const double* __rest
     lga = warp_sum(lga);
     const double lg_asum = lgamma(alpha_sum);
     double term = 0.;
-    for (int64_t d = warp0; d < D; d += nwarps) {
-        const double* g = gamma + d * ld;
+    const int64_t ngroups = (D + DPW - 1) / DPW;
+    for (int64_t w = warp0; w < ngroups; w += nwarps) {
+        const int64_t d = w * DPW + grp;
+        const bool live = d < D;  // the last warp's trailing groups idle (they still take part in the shuffles)
+        const double* g = gamma + (live ? d : 0) * ld;
         double s = 0.;
-        for (int k = lane; k < K; k += 32) s += g[k];
-        s = warp_sum(s);
+        for (int k = l; k < K; k += LPD) s += g[k];
+        s = group_sum<LPD>(s);
         double pt, lg_s;
         psi_lgamma_as103(s, pt, lg_s);
-        double t = 0., pp = 1.;  // pp: product of this lane's shift products (<= 32 factors in [1e-4, 4e5])
-        for (int k = lane; k < (int)ld; k += 32) {
+        double t = 0., pp = 1.;  // pp: product of this lane's shift products (each in [1e-4, 4e5])
+        int nf = 0;
+        for (int k = l; k < (int)ld; k += LPD) {
             if (k < K) {
                 const double gk = g[k];
                 double ps, lg, p;
                 psi_lgamma_as103_split(gk, ps, lg, p);
                 pp *= p;
+                if (++nf == 32) {  // keep the running product inside the double range for any K / LPD
+                    t -= log(pp);
+                    pp = 1.;
+                    nf = 0;
+                }
                 const double e = ps - pt;
                 t += (alpha_vec[k] - gk) * e + lg;
-                if (eT) eT[d * ld + k] = exp(e);
-            } else if (eT) {
+                if (eT && live) eT[d * ld + k] = exp(e);
+            } else if (eT && live) {
                 eT[d * ld + k] = 0.;
             }
         }
         t -= log(pp);  // sum_k lgamma(gamma_k) = sum_k Stirling_k - log(prod_k p_k): one log per lane
-        t = warp_sum(t);
-        term += t - lga + (lg_asum - lg_s);
+        t = group_sum<LPD>(t);
+        if (live && l == 0) term += t - lga + (lg_asum - lg_s);
     }
-    double v[1] = {lane == 0 ? term : 0.};
+    double v[1] = {term};
     block_sum<1>(v, sm);
     if (threadIdx.x == 0) {
         double* rec = records + (size_t)blockIdx.x * NPART;
@@ -213,9 +229,13 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
         return TTLDA_EWORKSPACE;
     }
     cudaStream_t s = (cudaStream_t)stream;
-    int grid = grid_for_warps(D, 8, 8);
-    theta_refresh_kernel<<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta,
-                                             (double*)workspace);
+    const int lpd = K > 256 ? 32 : (K > 128 ? 16 : (K > 32 ? 8 : 4));
+    int grid = grid_for_warps((D + 32 / lpd - 1) / (32 / lpd), 8, 8);
+    double* rec = (double*)workspace;
+    if (lpd == 32) theta_refresh_kernel<32><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
+    else if (lpd == 16) theta_refresh_kernel<16><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
+    else if (lpd == 8) theta_refresh_kernel<8><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
+    else theta_refresh_kernel<4><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
     TTLDA_LAUNCH_CHECK("theta_refresh");
     return launch_reduce_records((const double*)workspace, grid, partial_out, s);
 }
