@@ -98,7 +98,8 @@ int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, i
  * CSR arrays AND of the corpus-wide mirror arrays (blocks are contiguous in both).  rowptr_block = &rowptr[doc_base]
  * (D_block + 1 absolute offsets); colidx/counts/docidx/ccounts/csr2csc are the corpus-wide array bases;
  * colptr_block = &colptr[b * V] (V + 1 absolute offsets are written).  The result is identical to the block's slice
- * of ttlda_csr_to_csc(nblocks, block_docs = D_block).  Workspace: ttlda_csr_to_csc_workspace_bytes(nnz_block,..,1). */
+ * of ttlda_csr_to_csc(nblocks, block_docs = D_block).  ccounts may be NULL (the mirrored counts are only read by
+ * ttlda_sstats_csc_f64 without ratio_csc).  Workspace: ttlda_csr_to_csc_workspace_bytes(nnz_block,..,1). */
 int ttlda_csr_to_csc_block(const int64_t* rowptr_block, const int32_t* colidx, const int32_t* counts,
                            int64_t D_block, int64_t V, int64_t doc_base, int64_t pos_base, int64_t nnz_block,
                            int64_t* colptr_block, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc,

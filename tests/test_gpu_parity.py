@@ -480,9 +480,12 @@ def test_em_step_from_host_equals_resident_iteration(monkeypatch, blocks, handof
     for t in (c.colidx, c.counts, c.docidx, c.ccounts, c.csr2csc, c.colptr):
         t.fill_(-1)
     ps = [m.em_step_from_host(*h) for _ in range(3)]
-    for a, b in zip(mirror[:3] + (mirror[3:] if handoff == "1" else []),
-                    [c.colptr, c.docidx, c.ccounts] + ([c.csr2csc] if handoff == "1" else [])):
-        assert torch.equal(a, b)  # block-by-block mirror == one-call blocked mirror
+    # block-by-block mirror == one-call blocked mirror (with the ratio hand-off the mirrored counts are not rebuilt)
+    got = [c.colptr, c.docidx, c.csr2csc if handoff == "1" else c.ccounts]
+    want = [mirror[0], mirror[1], mirror[3] if handoff == "1" else mirror[2]]
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    assert c.ccounts_valid == (handoff == "0")
     assert relerr(ps, pr[:3]) < 1e-13  # perplexity of the incoming state of each iteration
     assert np.array_equal(m._gamma_, ref._gamma_) and np.array_equal(m._lambda_, ref._lambda_)
     assert m.inner_iterations == 2 * 900

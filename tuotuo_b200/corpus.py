@@ -93,11 +93,12 @@ class DeviceCorpus:
         nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
                       self.colptr, self.docidx, self.ccounts, ws, self.csr2csc if with_map else None)
         self.nblocks, self.block_docs = nblocks, block_docs
+        self.ccounts_valid = True
         del ws
 
     def ensure_csc(self, ld: int):
         nb, bd = self.plan_blocks(ld)
-        if self.colptr is None or (self.nblocks, self.block_docs) != (nb, bd):
+        if self.colptr is None or (self.nblocks, self.block_docs) != (nb, bd) or not getattr(self, "ccounts_valid", True):
             self.build_csc(nb, bd)
 
     # -- host views ----------------------------------------------------------------------------------------------------

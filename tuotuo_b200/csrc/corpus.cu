@@ -91,7 +91,7 @@ __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint
         if (i < nnz) {
             const int64_t p = spos[i];
             docidx[i] = (int32_t)docs[p];
-            ccounts[i] = counts[p];
+            if (ccounts) ccounts[i] = counts[p];  // NULL: the caller's statistics pass runs on the E-step's ratios
             if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + i);  // where CSR position p lives in the mirror
         }
     }
@@ -272,7 +272,7 @@ int ttlda_csr_to_csc_block(const int64_t* rowptr_block, const int32_t* colidx, c
                            int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(rowptr_block && colptr_block && workspace, "NULL pointer");
-    TTLDA_REQUIRE(nnz_block == 0 || (colidx && counts && docidx && ccounts), "NULL pointer");
+    TTLDA_REQUIRE(nnz_block == 0 || (colidx && docidx && (counts || !ccounts)), "NULL pointer");
     TTLDA_REQUIRE(nnz_block >= 0 && D_block >= 0 && V >= 0 && doc_base >= 0 && pos_base >= 0, "negative size");
     TTLDA_REQUIRE(pos_base + nnz_block < ((int64_t)1 << 32), "nnz per device must be < 2^32");
     TTLDA_REQUIRE(doc_base + D_block < ((int64_t)1 << 31), "documents per device must be < 2^31");

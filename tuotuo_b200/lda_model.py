@@ -267,6 +267,8 @@ class LDASmoothed:
         elif self._sstats_mode == "atomic":
             nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
         else:
+            if not (use_ratio and st.ratio is not None) and not getattr(c, "ccounts_valid", True):
+                c.build_csc(c.nblocks, c.block_docs)  # a streamed step left the mirrored counts stale
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
                           st.ratio if use_ratio else None)
         dist = self._dist()
@@ -382,7 +384,7 @@ class LDASmoothed:
                 nv.widen_i32(stage_ct[s:e], c.counts[s:e])
             colptr_b = c.colptr[b * V:b * V + V + 1]
             nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, colptr_b, c.docidx,
-                                c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
+                                None if use_ratio else c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
             nv.estep(c.rowptr[d0:d1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
                      st.eT[cur][d0:d1], st.eB, st.gamma[cur][d0:d1], st.gamma[nxt][d0:d1], None, e_num_step, 1e-05,
                      st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
@@ -391,6 +393,7 @@ class LDASmoothed:
             nv.sstats_csc_block(colptr_b, c.docidx, c.ccounts, V, K, s, e - s, st.eT[cur], st.eB,
                                 st.S_blocks[b] if nb > 1 else st.sstats, st.ws_s, st.ratio)
         c.nnz = nnz
+        c.ccounts_valid = not use_ratio  # the mirrored counts are not rebuilt when the statistics use the ratios
         if nb > 1:
             nv.sstats_fold(st.S_blocks, st.sstats)
         st.part[0].copy_(acc)
