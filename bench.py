@@ -344,8 +344,8 @@ def run_ours(args):
                         "ms_per_step": e2e_ms, "steps": n_e2e, "host_dtypes": e2e_main["host_dtypes"],
                         "int32": e2e_res["int32"],
                         "what": "LDASmoothed.em_step_from_host: pinned-host CSR -> device one document block at a time; "
-                                "per block CSC mirror + E-step + statistics overlap the next block's upload; then "
-                                "fold, theta refresh, M-step, perplexity terms -> host"},
+                                "per block CSC mirror + E-step overlap the next block's upload; then statistics, "
+                                "theta refresh, M-step, perplexity terms -> host"},
                 "roofline": roofline, "cpu_baseline": cpu,
                 "perplexity_trace": [round(p, 6) for p in perps[:8]]}
         print(json.dumps(line), flush=True)

@@ -296,10 +296,9 @@ class LDASmoothed:
         """One EM iteration (lda_model.py:285-316 + the perplexity of the incoming state, :403-409) on a CSR corpus
         that lives in host memory (torch CPU tensors, ideally pinned): rowptr int64[D+1], colidx/counts int32[nnz]
         — or compact: colidx uint16/int16 bit patterns when V <= 65536, counts uint8 or uint16, widened on the device —
-        same D and V as the fitted corpus.  Everything is pipelined per DOCUMENT BLOCK of the blocked mirror: while
-        block b+1 crosses PCIe on a copy stream, block b is mirrored (ttlda_csr_to_csc_block), E-stepped (leaving c/N
-        per nonzero in mirror order) and accumulated into its partial statistics (ttlda_sstats_csc_block_f64); the
-        partials are folded in block order, then theta refresh and M-step.  Bit-identical to uploading the corpus
+        same D and V as the fitted corpus.  The upload is pipelined per DOCUMENT BLOCK of the blocked mirror: while
+        block b+1 crosses PCIe on a copy stream, block b is mirrored (ttlda_csr_to_csc_block) and E-stepped (leaving
+        c/N per nonzero in mirror order); then one statistics pass, theta refresh and M-step.  Bit-identical to uploading the corpus
         and running one iteration of `fit`.  Returns the perplexity of the incoming state on this corpus.  This is
         the per-step path `bench.py` times as `e2e`.  (`chunks` is accepted for compatibility and ignored: the
         pipeline granularity is the mirror's document block.)"""
@@ -329,13 +328,9 @@ class LDASmoothed:
             c.csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
         if st.ratio is not None and st.ratio.numel() < max(nnz, 1):
             st.ratio = torch.empty(nnz, dtype=torch.float64, device=dev)
-        # statistics workspace: head for one block's pass; the per-block partials live where the one-call pass keeps
-        # them, in the tail of the same workspace
-        tail = nb * V * ld * 8 if nb > 1 else 0
-        if st.ws_s.numel() < nv.sstats_workspace_bytes(max_blk, V, ld, 1) + tail or (st.ws_s.numel() - tail) % 8:
-            st.ws_s = torch.empty(nv.sstats_workspace_bytes(max(nnz, c.nnz), V, ld, nb), dtype=torch.uint8, device=dev)
-        if nb > 1:
-            st.S_blocks = st.ws_s[st.ws_s.numel() - tail:].view(torch.float64).view(nb, V, ld)
+        need = nv.sstats_workspace_bytes(nnz, V, ld, nb)
+        if st.ws_s.numel() < need:
+            st.ws_s = torch.empty(need, dtype=torch.uint8, device=dev)
         need = nv.csr_to_csc_workspace_bytes(max_blk, bd, V, 1)
         if getattr(st, "ws_c", None) is None or st.ws_c.numel() < need:
             st.ws_c = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -390,12 +385,11 @@ class LDASmoothed:
                      st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
             acc += st.part[0]
             it_acc += st.iters
-            nv.sstats_csc_block(colptr_b, c.docidx, c.ccounts, V, K, s, e - s, st.eT[cur], st.eB,
-                                st.S_blocks[b] if nb > 1 else st.sstats, st.ws_s, st.ratio)
         c.nnz = nnz
         c.ccounts_valid = not use_ratio  # the mirrored counts are not rebuilt when the statistics use the ratios
-        if nb > 1:
-            nv.sstats_fold(st.S_blocks, st.sstats)
+        # one statistics pass over the whole mirror: its ticket order already walks the blocks one L2 window at a time,
+        # and the GPU, not PCIe, bounds this step — per-block passes (ttlda_sstats_csc_block_f64) cost 2.3 ms more
+        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, nnz, nb, st.eT[cur], st.eB, st.sstats, st.ws_s, st.ratio)
         st.part[0].copy_(acc)
         st.iters.copy_(it_acc)
         self.inner_iterations, capped = self._collect(tok_row=0)
