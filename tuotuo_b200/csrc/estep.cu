@@ -179,23 +179,21 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
             auto body = [&](int s, const KSlice<G, E>& row) {
                 const int i = s * R + r;                          // nonzero handled by this group in this sub-batch
                 const int c = __shfl_sync(0xffffffffu, my_c, i);  // 0 for i >= cnt: the group idles harmlessly
-                const double p = group_sum<G>(t.dot(row));
-                if (ESTEP) {
-                    const double rr = fast_div_pos((double)c, p + 1e-100);
-                    acc.axpy(rr, row);
-                }
+                // N = theta.beta + 1e-100 (lda_model.py:242): the 1e-100 enters as the start value of one DFMA chain
+                // (1e-100 / G per lane is exact, G a power of two) instead of as one more dependent DADD
+                const double p = group_sum<G>(t.dot(row, ESTEP ? 1e-100 / G : 0.));
+                if (ESTEP) acc.axpy(fast_div_pos((double)c, p), row);
                 // hand p back to the lane that loaded nonzero `lane` (group lane % R of sub-batch lane / R)
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == s) my_p = pv;
             };
             if (PREFETCH) walk_rows_carried<G, E>(P.eB, ld, my_w, cnt, nx_w, n0 + 32 < e, rowA, g, r, last_ok, body);
             else walk_rows<G, E, false>(P.eB, ld, my_w, cnt, g, r, last_ok, body);
-            if (lane < cnt) {  // one log per nonzero
-                tok_acc += (double)my_c * log(my_p);
+            if (lane < cnt) {  // one log per nonzero (of theta.beta itself: the token term has no 1e-100, :125-139)
+                tok_acc += (double)my_c * log(ESTEP ? my_p - 1e-100 : my_p);
                 cnt_acc += (double)my_c;
                 // leave c/N for the statistics pass, in mirror (word-major) order: one scattered 8-byte store
-                if (ESTEP && P.ratio_csc)
-                    st_stream_f64(P.ratio_csc + (uint32_t)my_pos, (double)my_c / (my_p + 1e-100), pol);
+                if (ESTEP && P.ratio_csc) st_stream_f64(P.ratio_csc + (uint32_t)my_pos, (double)my_c / my_p, pol);
             }
         }
 

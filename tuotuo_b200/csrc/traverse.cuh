@@ -42,10 +42,10 @@ struct KSlice {
 #pragma unroll
         for (int j = 0; j < E; ++j) v[j] = make_double2(0., 0.);
     }
-    // partial dot product over this lane's slices
-    __device__ __forceinline__ double dot(const KSlice& o) const
+    // partial dot product over this lane's slices (+ init: lets the caller fold a constant into the sum for free)
+    __device__ __forceinline__ double dot(const KSlice& o, double init = 0.) const
     {
-        double p0 = 0., p1 = 0., p2 = 0., p3 = 0.;  // four independent DFMA chains
+        double p0 = init, p1 = 0., p2 = 0., p3 = 0.;  // four independent DFMA chains
 #pragma unroll
         for (int j = 0; j < E; ++j) {
             if (j & 1) {
@@ -144,12 +144,34 @@ __device__ __forceinline__ void walk_rows_carried(const double* __restrict__ tab
     }
 }
 
-// sum over the G lanes of a group (result in every lane of the group)
+// Sum over each aligned quad of lanes on the FP64 tensor core: one DMMA m8n8k4 against a matrix of ones
+// (A[lane / 4][lane % 4] = this lane's value, B = 1, C = 0  =>  D[lane / 4][*] = the quad's sum, in every lane of
+// the quad).  It replaces two dependent shuffle + add steps — each a 64-bit SHFL pair and a ~30-cycle DADD that an
+// in-order warp cannot issue past — on the dot -> reduce -> divide -> axpy chain of every sub-batch
+// (tools/membench7.cu: a lone warp's sub-batch drops from 738 to 547 cycles, 12 warps/SM go from 11.8 to 14.2 TB/s).
+// Must be executed by all 32 lanes (mma.sync).
+__device__ __forceinline__ double quad_sum_mma(double p)
+{
+    double d0, d1;
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(p), "d"(1.0), "d"(0.0), "d"(0.0));
+    (void)d1;
+    return d0;
+}
+
+// sum over the G lanes of a group (result in every lane of the group; identical bits in all of them).  Warp-uniform.
 template <int G>
 __device__ __forceinline__ double group_sum(double p)
 {
+    if constexpr (G >= 4) {
+        p = quad_sum_mma(p);
 #pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        for (int o = 4; o < G; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    } else {
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    }
     return p;
 }
 

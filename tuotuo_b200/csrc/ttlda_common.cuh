@@ -159,16 +159,19 @@ __device__ __forceinline__ double psi_exact(double x)
 }
 
 // c / x for a normal positive x, without the IEEE division's special-case path: hardware reciprocal approximation
-// (MUFU.RCP64H, ~2^-23) + two Newton steps + the multiply = 5 dependent FP64 operations instead of ~9 plus a branch.
-// Result within ~2 ulp of the correctly rounded quotient — the parity budget on gamma / lambda is 1e-9 relative.
-// The division sits on the critical path of every sub-batch (tools/membench2.cu: +24 % when it is added).
+// y0 (MUFU.RCP64H, relative error e ~ 2^-23) corrected as c*y0*(1 + e + e^2), e = 1 - x*y0 (error e^3 ~ 1e-21, then
+// rounding: within ~2 ulp of the correctly rounded quotient; the parity budget on gamma / lambda is 1e-9 relative).
+// The division sits on the dependent chain of every sub-batch, and a dependent FP64 operation costs ~30 cycles on this
+// part (tools/membench7.cu: a lone warp needs ~750 cycles of chain per sub-batch): this form is 3 levels deep after
+// the MUFU (e | c*y0 -> e + e^2 -> fma) where two Newton steps + the multiply are 5, the IEEE division ~9 and a branch.
 __device__ __forceinline__ double fast_div_pos(double c, double x)
 {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = y * fma(-x, y, 2.);
-    y = y * fma(-x, y, 2.);
-    return c * y;
+    const double e = fma(-x, y, 1.);
+    const double r = c * y;
+    const double e2 = fma(e, e, e);
+    return fma(r, e2, r);
 }
 
 // 16-byte global loads of a K-vector slice.  The beta tables are re-read by many documents: keep them on the
