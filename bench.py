@@ -314,6 +314,13 @@ def run_ours(args):
                 "kernel_ms_all": {k: round(v, 4) for k, v in per_kernel.items()},
                 "iteration_frac": ab["iteration"] / (ms_per_step * 1e-3) / 1e9 / peak,
                 "note": "gathers of the 8*K*V-byte exp(E[log beta]) table are L2 hits when it fits the 126 MB L2"}
+    if 8 * K * V <= 100e6:
+        # the table the dominant kernel gathers from is L2-resident: the relevant ceiling is the L2 -> SM path,
+        # 64 B/clk/SM (tools/membench2.cu level 0 / membench7.cu: 16.5-18.5 TB/s measured for this traversal)
+        l2_peak = 64.0 * 148 * 1.92
+        roofline["l2_gather"] = {"peak": l2_peak, "unit": "GB/s", "frac": achieved / l2_peak,
+                                 "source": "64 B/clk/SM x 148 SMs x 1.92 GHz; tools/membench2.cu level 0 measures "
+                                           "16.5-18.5 TB/s for the same traversal (DESIGN.md section 4)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:  # reported at N=1 only (bench contract)
