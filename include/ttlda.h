@@ -218,6 +218,15 @@ int ttlda_mstep_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, doub
                     double* exp_elogbeta, double* lambda, double* elogbeta_out, double* colsum_out,
                     double* partial_out, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Online (stochastic) M-step — Hoffman, Blei & Bach, "Online Learning for LDA" (2010), eq. 7-9; the reference only
+ * lists it as roadmap (readme.md:131-136), its `sampling=True` has no update rule:
+ *      lambda <- (1 - rho) * lambda + rho * (eta + scale * sstats * exp_elogbeta),   scale = D_population / |minibatch|
+ * then the same exp_elogbeta refresh and beta-prior record as ttlda_mstep_f64 (which is rho = scale = 1). */
+int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, double eta, double scale,
+                           double rho, double* exp_elogbeta, double* lambda, double* elogbeta_out,
+                           double* colsum_out, double* partial_out,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
 /* beta refresh from an existing lambda (initial state, or after a hyper-parameter update):
  * exp_elogbeta = exp(dirichlet_expectation over the vocabulary of lambda[:,k]) and the beta-prior term.
  * Replaces: _dirichlet_expectation_2d(self._lambda_) at tuotuo/lda_model.py:120 and the term at :157-163. */

@@ -412,6 +412,29 @@ class OracleLDA:
             perplexities.append(perp)
         return perplexities
 
+    # -- NOT in the reference (readme.md:131-136 roadmap): restates LDASmoothed.partial_fit of the CUDA build ----------
+    def partial_fit(self, X: CSRCorpus, total_docs=None, tau0=1.0, kappa=0.7, e_num_step=100):
+        """Online VB (Hoffman, Blei & Bach 2010, Alg. 2) on one minibatch; returns the minibatch perplexity bound under
+        the converged gamma and the topics before the update (document part scaled by total_docs / |B|)."""
+        assert self.inner_fixed_point, "online steps solve each document to its fixed point"
+        K, V, D = self.K, X.V, X.D
+        total = int(total_docs) if total_docs else D
+        if not hasattr(self, "t_online"):
+            np.random.seed(SEED)
+            self.lam = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(np.float64, copy=False)
+            self.t_online = 0
+        self.M, self.V = D, V
+        self.gamma = np.ascontiguousarray(self.alpha + np.ones((D, K), dtype=np.float64) * V / K)
+        Elogtheta = dirichlet_expectation_2d(self.gamma, self.engine)
+        Elogbeta = dirichlet_expectation_2d(self.lam, self.engine)
+        self.gamma, (S, Elogtheta) = self.e_step(X, Elogtheta, Elogbeta, e_num_step)
+        self.D_population = total
+        perp, _ = self.approx_perplexity(X, True, Elogtheta, Elogbeta)
+        rho = (tau0 + self.t_online) ** (-kappa)
+        self.lam = (1.0 - rho) * self.lam + rho * (self.eta + (total / D) * S)
+        self.t_online += 1
+        return perp
+
     # -- lda_model.py:435-509 ------------------------------------------------------------------------------
     def update_alpha(self, step=500, threshold=1e-07):
         it = 0

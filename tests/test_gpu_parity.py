@@ -582,6 +582,36 @@ def test_block_entry_points_equal_one_call_forms(nv, dev):
             assert torch.equal(S, S_ref)
 
 
+@pytest.mark.parametrize("K,V", [(12, 300), (100, 800)])
+def test_partial_fit_online_vs_oracle(K, V):
+    """Online VB (partial_fit): three minibatches of different sizes, topics persisting across calls, against the
+    oracle's restatement — gamma, lambda, minibatch perplexity bound; then the topics keep serving approx_perplexity."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    m = LDASmoothed(K, verbose=False)
+    o = OracleLDA(K, inner_fixed_point=True)
+    total = 5000
+    for i, D in enumerate((150, 90, 220)):
+        rp, ci, ct = numpy_corpus(100 + i, D, V, min(K, 10), 60, ragged=True)
+        p = m.partial_fit(Document.from_csr(rp, ci, ct, V), total_docs=total, tau0=2.0, kappa=0.6, return_perplexity=True)
+        po = o.partial_fit(CSRCorpus(rp, ci, ct, V), total_docs=total, tau0=2.0, kappa=0.6)
+        assert relerr(p, po) < 1e-8
+        assert relerr(m._gamma_, o.gamma) < 1e-9 and relerr(m._lambda_, o.lam) < 1e-9
+    assert m._online_t == 3 and m._gamma_.shape == (220, K)
+    # asynchronous form (no perplexity, nothing read back) gives the same update
+    m2 = LDASmoothed(K, verbose=False)
+    for i, D in enumerate((150, 90, 220)):
+        rp, ci, ct = numpy_corpus(100 + i, D, V, min(K, 10), 60, ragged=True)
+        assert m2.partial_fit(Document.from_csr(rp, ci, ct, V), total_docs=total, tau0=2.0, kappa=0.6) is None
+    assert np.array_equal(m2._lambda_, m._lambda_)
+    with pytest.raises(ValueError):
+        m.partial_fit(Document.from_csr(rp, ci, ct, V), kappa=0.5)
+    with pytest.raises(ValueError):
+        m.partial_fit(Document.from_csr(rp, ci, ct, V + 1))
+
+
 EDGE = [
     # (K, V, rows as lists of (word, count))
     (1, 1, [[(0, 3)]]),                                   # one topic, one word, one document

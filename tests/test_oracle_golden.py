@@ -143,3 +143,20 @@ def test_estep_iteration_cap_warns_like_reference(golden_dir):
         gam, _ = m.e_step(X, g["Elogtheta0"], g["Elogbeta0"], step=0)
         assert m.capped_docs == X.D and m.inner_iters == X.D
         assert relerr(gam, g["gamma1"]) < 1e-13
+
+
+def test_online_step_reduces_to_batch_step():
+    """OracleLDA.partial_fit (online VB, not in the reference) with rho = 1 and |B| = D is one fixed-point EM step."""
+    import lda_oracle as orc
+
+    rng = np.random.default_rng(5)
+    X = orc.CSRCorpus.from_dense(rng.poisson(0.3, size=(40, 30)).astype(np.float64))
+    a = orc.OracleLDA(4, inner_fixed_point=True)
+    a.partial_fit(X, total_docs=X.D, tau0=1.0, kappa=0.7)  # rho_0 = 1
+    b = orc.OracleLDA(4, inner_fixed_point=True)
+    b.fit(X, em_num_step=1, update_hyper_parms=False)
+    assert np.max(np.abs(a.lam - b.lam) / np.abs(b.lam)) < 1e-13
+    assert np.max(np.abs(a.gamma - b.gamma) / np.abs(b.gamma)) < 1e-13
+    lam1 = a.lam.copy()
+    a.partial_fit(X, total_docs=4 * X.D, tau0=1.0, kappa=0.7)  # rho_1 = 2^-0.7: a proper blend
+    assert a.t_online == 2 and not np.allclose(a.lam, lam1)

@@ -52,6 +52,8 @@ SIGNATURES = {
     "ttlda_sstats_fold_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
     "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_mstep_online_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _f64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr,
+                                              _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
                                               _ptr]),
     "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
@@ -78,7 +80,7 @@ KERNELS_PER_CALL = {
     "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1,
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
-    "ttlda_mstep_f64": 4,
+    "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
 }
@@ -280,6 +282,13 @@ def mstep(sstats, K, eta, eB, lam, elogbeta, colsum, partial, ws):
     V, ld = sstats.shape
     _call("ttlda_mstep_f64", _p(sstats, f64), V, int(K), ld, float(eta), _p(eB, f64), _p(lam, f64), _p(elogbeta, f64),
           _p(colsum, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def mstep_online(sstats, K, eta, scale, rho, eB, lam, elogbeta, colsum, partial, ws):
+    V, ld = sstats.shape
+    _call("ttlda_mstep_online_f64", _p(sstats, f64), V, int(K), ld, float(eta), float(scale), float(rho), _p(eB, f64),
+          _p(lam, f64), _p(elogbeta, f64), _p(colsum, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(),
+          _stream())
 
 
 def beta_refresh(lam, K, eta, eB, elogbeta, colsum, partial, ws):

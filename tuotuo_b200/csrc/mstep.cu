@@ -17,10 +17,13 @@ constexpr int kColBlocks = 592;  // 148 SMs x 4: CTAs of the column-sum pass (fi
 constexpr int kMaxJ = 8;         // columns per thread: ld <= TX * kMaxJ with TX >= 128 for ld > 64
 
 // blockDim = (TX, 256/TX).  Thread (tx,ty) owns columns k = tx + TX*j and words w0+ty, w0+ty+TY, ...
-template <bool FROM_SSTATS>
+// MODE 0: column sums of an existing lambda;  1: lambda = eta + S*eB (batch M-step);  2: online blend
+// lambda = (1 - rho) * lambda + rho * (eta + scale * S*eB)   (Hoffman, Blei & Bach 2010, eq. 7-9)
+template <int MODE>
 __global__ void __launch_bounds__(256) mstep_lambda_kernel(const double* __restrict__ S, const double* __restrict__ eB,
                                                            double* __restrict__ lambda, int64_t V, int K, int64_t ld,
-                                                           double eta, double* __restrict__ colpart)
+                                                           double eta, double scale, double rho,
+                                                           double* __restrict__ colpart)
 {
     extern __shared__ double sm_cols[];  // [TY][ld]
     const int TX = blockDim.x, TY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
@@ -36,8 +39,11 @@ __global__ void __launch_bounds__(256) mstep_lambda_kernel(const double* __restr
             if (k < (int)ld) {
                 const int64_t idx = w * ld + k;
                 double lam;
-                if (FROM_SSTATS) {
+                if (MODE == 1) {
                     lam = (k < K) ? eta + S[idx] * eB[idx] : 0.;  // lda_model.py:264 then :280
+                    lambda[idx] = lam;
+                } else if (MODE == 2) {
+                    lam = (k < K) ? fma(rho, fma(scale, S[idx] * eB[idx], eta), (1. - rho) * lambda[idx]) : 0.;
                     lambda[idx] = lam;
                 } else {
                     lam = (k < K) ? lambda[idx] : 0.;
@@ -128,8 +134,9 @@ static int64_t mstep_ws_bytes(int64_t ld)
                      align256((size_t)ld * sizeof(double)) + 256);
 }
 
-template <bool FROM_SSTATS>
-static int run_mstep(const double* S, int64_t V, int64_t K, int64_t ld, double eta, double* eB, double* lambda,
+template <int MODE>
+static int run_mstep(const double* S, int64_t V, int64_t K, int64_t ld, double eta, double scale, double rho, double* eB,
+                     double* lambda,
                      double* elogbeta, double* colsum_out, double* partial_out, void* workspace,
                      int64_t workspace_bytes, cudaStream_t s)
 {
@@ -149,7 +156,8 @@ static int run_mstep(const double* S, int64_t V, int64_t K, int64_t ld, double e
     const int TY = 256 / TX;
     int nblocks = (int)(V < kColBlocks ? (V > 0 ? V : 1) : kColBlocks);
     const size_t smem = (size_t)TY * ld * sizeof(double);
-    mstep_lambda_kernel<FROM_SSTATS><<<nblocks, dim3(TX, TY), smem, s>>>(S, eB, lambda, V, (int)K, ld, eta, colpart);
+    mstep_lambda_kernel<MODE><<<nblocks, dim3(TX, TY), smem, s>>>(S, eB, lambda, V, (int)K, ld, eta, scale, rho,
+                                                                   colpart);
     TTLDA_LAUNCH_CHECK("mstep_lambda");
     // eta is a scalar prior: np.sum(eta) is eta itself
     colsum_finish_kernel<<<1, 256, 0, s>>>(colpart, nblocks, (int)K, ld, eta, colsum_out, psi_colsum, extra);
@@ -180,8 +188,19 @@ int ttlda_mstep_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, doub
 {
     TTLDA_REQUIRE(sstats && exp_elogbeta && lambda && colsum_out && partial_out && workspace, "NULL pointer");
     TTLDA_REQUIRE(V >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
-    return run_mstep<true>(sstats, V, K, ld, eta, exp_elogbeta, lambda, elogbeta_out, colsum_out, partial_out,
-                           workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_mstep<1>(sstats, V, K, ld, eta, 1., 1., exp_elogbeta, lambda, elogbeta_out, colsum_out, partial_out,
+                        workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t ld, double eta, double scale, double rho,
+                           double* exp_elogbeta, double* lambda, double* elogbeta_out, double* colsum_out,
+                           double* partial_out, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(sstats && exp_elogbeta && lambda && colsum_out && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(V >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
+    TTLDA_REQUIRE(rho > 0. && rho <= 1. && scale > 0., "need 0 < rho <= 1 and scale > 0");
+    return run_mstep<2>(sstats, V, K, ld, eta, scale, rho, exp_elogbeta, lambda, elogbeta_out, colsum_out, partial_out,
+                        workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t ld, double eta, double* exp_elogbeta,
@@ -190,8 +209,8 @@ int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t l
 {
     TTLDA_REQUIRE(lambda && exp_elogbeta && colsum_out && partial_out && workspace, "NULL pointer");
     TTLDA_REQUIRE(V >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
-    return run_mstep<false>(nullptr, V, K, ld, eta, exp_elogbeta, const_cast<double*>(lambda), elogbeta_out,
-                            colsum_out, partial_out, workspace, workspace_bytes, (cudaStream_t)stream);
+    return run_mstep<0>(nullptr, V, K, ld, eta, 1., 1., exp_elogbeta, const_cast<double*>(lambda), elogbeta_out,
+                        colsum_out, partial_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

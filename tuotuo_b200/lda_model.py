@@ -123,7 +123,9 @@ class LDASmoothed:
         st = self._st
         st.alpha_vec = torch.as_tensor(self._alpha_vec_host().copy()).to(st.dev)
 
-    def _alloc_state(self, corpus: DeviceCorpus):
+    def _alloc_state(self, corpus: DeviceCorpus, topics_from=None):
+        """Device tensors for `corpus`.  topics_from: a previous state whose topic-side tables (lambda, exp(E[log beta]),
+        column sums, beta-prior record) are carried over (online learning: the documents change, the topics persist)."""
         dev = corpus.device
         nv.check_device(dev)
         K, V, D = int(self.K), corpus.V, corpus.D
@@ -152,6 +154,11 @@ class LDASmoothed:
             if self._ratio_handoff and not self._inner_fixed_point:
                 # c/N per nonzero, written by the E-step in mirror order, consumed by the statistics pass
                 st.ratio = torch.empty(max(corpus.nnz, 1), dtype=f64, device=dev)
+        if topics_from is not None:
+            if (topics_from.K, topics_from.V, topics_from.dev) != (K, V, dev):
+                raise ValueError("the minibatch must have the vocabulary size / device of the model being updated")
+            st.lam, st.eB, st.colsum, st.ws_m = topics_from.lam, topics_from.eB, topics_from.colsum, topics_from.ws_m
+            st.part[2].copy_(topics_from.part[2])
         st.terms = dict(tok=0.0, theta=0.0, beta=0.0, count=0.0)
         self._st = st
         self._np_cache = {}
@@ -255,7 +262,7 @@ class LDASmoothed:
                      st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
 
-    def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False):
+    def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False, online=None):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
         adopt the E-step's gamma / exp(E[log theta]).  have_sstats: st.sstats already holds this rank's statistics
         (the block-pipelined streaming path)."""
@@ -284,7 +291,11 @@ class LDASmoothed:
             st.part[1, 0].copy_(st.part[4, 0])
         if work is not None:
             work.wait()
-        nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
+        if online is None:
+            nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
+        else:  # (scale, rho): stochastic natural-gradient step on lambda (partial_fit)
+            nv.mstep_online(st.sstats, st.K, float(self._eta_), online[0], online[1], st.eB, st.lam, None, st.colsum,
+                            st.part[2], st.ws_m)
         st.cur ^= 1
         self._invalidate()
 
@@ -397,6 +408,82 @@ class LDASmoothed:
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
         self._commit_iteration(have_sstats=True)
+        return perplexity
+
+    # ------------------------------------------------------------------------------------------------------------------
+    # online learning (the reference's roadmap item, readme.md:131-136)
+    # ------------------------------------------------------------------------------------------------------------------
+    def partial_fit(self, minibatch, total_docs: int = None, tau0: float = 1.0, kappa: float = 0.7,
+                    e_num_step: int = 100, return_perplexity: bool = False):
+        """One step of online variational Bayes (Hoffman, Blei & Bach 2010, Algorithm 2) on a minibatch of documents.
+
+        E-step: every document's gamma is iterated to its fixed point against the current topics
+        (ttlda_estep_fixed_point_f64, gamma_0 = alpha + V/K as in lda_model.py:364); M-step:
+            lambda <- (1 - rho_t) lambda + rho_t (eta + (D/|B|) * sstats),   rho_t = (tau0 + t)^(-kappa)
+        (ttlda_mstep_online_f64), D = total_docs (default: Document.num_doc_population), t = number of earlier calls.
+        The topics persist across calls; lambda_0 is the reference's (seed 42, Gamma(100, .01)).  The reference has no
+        such update (its `sampling=True` only rescales the ELBO): this is what gives it one.  With sharded minibatches
+        (torch.distributed) the statistics are summed over ranks as in fit().
+
+        return_perplexity: also return the per-word perplexity bound of the minibatch (document part scaled by D/|B| as
+        lda_model.py:152-153,187-188 do) under the converged gamma and the topics BEFORE this update — costs one more
+        token pass and a device->host read; otherwise the call is fully asynchronous and returns None."""
+        if not (0.5 < kappa <= 1.0) or tau0 < 0 or (tau0 == 0 and not hasattr(self, "_online_t")):
+            raise ValueError("online LDA needs kappa in (0.5, 1] and tau0 >= 0 (tau0 > 0 for the first step)")
+        doc = self._as_document(minibatch)
+        corpus = doc.device_corpus(self._dev())
+        dist = self._dist()
+        n_mb = corpus.D
+        if dist is not None:
+            t = torch.tensor([corpus.D], dtype=torch.int64, device=corpus.device)
+            dist.all_reduce(t)
+            n_mb = int(t.item())
+        if n_mb == 0:
+            raise ValueError("empty minibatch")
+        total = int(total_docs) if total_docs else max(int(doc.num_doc_population), n_mb)
+        if not hasattr(self, "V"):
+            self.V = doc.V
+        if self.V != doc.V:
+            raise ValueError("the minibatch vocabulary size differs from the model's")
+        if not hasattr(self, "train_doc"):
+            self.train_doc = doc
+        first = getattr(self, "_online_t", None) is None or self._st is None
+        saved = self._inner_fixed_point
+        self._inner_fixed_point = True  # documents are solved to their fixed point, not with the frozen-theta loop
+        try:
+            st = self._alloc_state(corpus, topics_from=None if first else self._st)
+            K, V = st.K, st.V
+            if first:
+                np.random.seed(SEED)  # lda_model.py:356-357
+                lam0 = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(DTYPE, copy=False)
+                nv.transpose_pad(torch.as_tensor(lam0).to(st.dev), st.lam)
+                self._refresh_beta()
+                self._online_t = 0
+            st.gamma[st.cur].zero_()  # lda_model.py:364
+            st.gamma[st.cur][:, :K] = st.alpha_vec + float(V) / float(K)
+            self._refresh_theta()
+            self._estep_speculative(e_num_step)
+            perplexity = None
+            if return_perplexity:
+                c, nxt = st.corpus, st.cur ^ 1
+                nv.elbo_tokens(c.rowptr, c.colidx, c.counts, K, st.eT[nxt], st.eB, st.part[3], st.ws)
+                buf = torch.stack([st.part[3, 0], st.part[0, 1], st.part[3, 2], st.iters[0].to(torch.float64),
+                                   st.iters[1].to(torch.float64), st.part[2, 0]])
+                if dist is not None:
+                    dist.all_reduce(buf[:5])
+                h = buf.cpu().numpy()
+                self.inner_iterations = int(h[3])
+                if int(h[4]):
+                    warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {int(h[4])} documents")
+                scale = total / n_mb
+                elbo = (float(h[0]) + float(h[1])) * scale + float(h[5])
+                self._last_elbo = elbo
+                perplexity = float(np.exp(np_clip_for_exp(-elbo / (np.float64(h[2]) * scale))))
+            rho = float((tau0 + self._online_t) ** (-kappa))
+            self._commit_iteration(online=(total / n_mb, rho))
+            self._online_t += 1
+        finally:
+            self._inner_fixed_point = saved
         return perplexity
 
     def _collect(self, tok_row: int):
