@@ -189,11 +189,14 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
  * ttlda_csr_to_csc): colptr_block = &colptr[b * V] (absolute offsets), docidx / ccounts / ratio_csc / exp_elogtheta
  * are the corpus-wide bases, sstats_block [V][ld] receives the block's partial statistics;
  * ttlda_sstats_fold_f64 then sums the nblocks partials [nblocks][V][ld] in block order into sstats [V][ld] —
- * bit-identical to the one-call form.  Workspace: ttlda_sstats_workspace_bytes(nnz_block, V, ld, 1). */
+ * bit-identical to the one-call form.  accumulate != 0: sstats_block is added to instead of overwritten — calling the
+ * blocks in order on ONE [V][ld] table (accumulate = 0 for the first) gives the same bits without any per-block
+ * buffers: the form for tables whose nblocks * V * ld partials would not fit (K*V and K*D both >> L2).
+ * Workspace: ttlda_sstats_workspace_bytes(nnz_block, V, ld, 1). */
 int ttlda_sstats_csc_block_f64(const int64_t* colptr_block, const int32_t* docidx, const int32_t* ccounts,
                                int64_t D, int64_t V, int64_t K, int64_t ld, int64_t pos_base, int64_t nnz_block,
                                const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
-                               double* sstats_block,
+                               double* sstats_block, int accumulate,
                                void* workspace, int64_t workspace_bytes, void* stream);
 int ttlda_sstats_fold_f64(const double* sstats_blocks, int64_t nblocks, int64_t V, int64_t ld, double* sstats,
                           void* stream);

@@ -580,6 +580,38 @@ def test_block_entry_points_equal_one_call_forms(nv, dev):
             S = torch.empty_like(S_ref)
             nv.sstats_fold(Sb, S)
             assert torch.equal(S, S_ref)
+            # serial form: the blocks accumulate into ONE table, no per-block buffers — same bits again
+            S2 = torch.full_like(S_ref, float("nan"))
+            for b in range(nb):
+                d0, d1 = b * bd, min((b + 1) * bd, D)
+                s, e = int(rowptr[d0]), int(rowptr[d1])
+                nv.sstats_csc_block(ref[0][b * V:b * V + V + 1], ref[1], ref[2], V, K, s, e - s, eT, eB, S2, ws_s, r,
+                                    accumulate=b > 0)
+            assert torch.equal(S2, S_ref)
+
+
+@pytest.mark.parametrize("handoff", ["1", "0"])
+def test_serial_block_statistics_equal_folded(monkeypatch, handoff):
+    """Serial-block mode (one launch per document block accumulating in place: the cfg5-class form without per-block
+    buffers) gives the bits of the folded one-launch form, in fit() and in the streamed step."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    monkeypatch.setenv("TTLDA_RATIO_HANDOFF", handoff)
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", "5")
+    rp, ci, ct = numpy_corpus(71, 700, 900, 15, 70, ragged=True)
+    res = {}
+    for serial in ("0", "1"):
+        monkeypatch.setenv("TTLDA_SERIAL_BLOCKS", serial)
+        m = LDASmoothed(36, verbose=False)
+        p = m.fit(Document.from_csr(rp, ci, ct, 900), em_num_step=3, return_perplexities=True)
+        assert m._st.corpus.serial_blocks == (serial == "1") and m._st.corpus.nblocks == 5
+        h = [torch.as_tensor(a).pin_memory() for a in (rp, ci, ct)]
+        p.append(m.em_step_from_host(*h))
+        res[serial] = (p, m._lambda_.copy(), m._gamma_.copy())
+    assert res["0"][0] == res["1"][0]
+    assert np.array_equal(res["0"][1], res["1"][1]) and np.array_equal(res["0"][2], res["1"][2])
 
 
 @pytest.mark.parametrize("K,V", [(12, 300), (100, 800)])

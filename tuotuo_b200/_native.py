@@ -48,7 +48,7 @@ SIGNATURES = {
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
                                             _ptr, _ptr, _i64, _ptr]),
     "ttlda_sstats_csc_block_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
-                                                  _ptr, _ptr, _i64, _ptr]),
+                                                  _ptr, ctypes.c_int, _ptr, _i64, _ptr]),
     "ttlda_sstats_fold_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
     "ttlda_mstep_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_mstep_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
@@ -255,12 +255,14 @@ def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, 
           int(nblocks), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
-def sstats_csc_block(colptr_block, docidx, ccounts, V, K, pos_base, nnz_block, eT, eB, sstats_block, ws, ratio_csc=None):
-    """Statistics of one document block ([V][ld] partial); docidx/ccounts/ratio_csc/eT are the corpus-wide arrays."""
+def sstats_csc_block(colptr_block, docidx, ccounts, V, K, pos_base, nnz_block, eT, eB, sstats_block, ws, ratio_csc=None,
+                     accumulate=False):
+    """Statistics of one document block ([V][ld] partial, or added to sstats_block when accumulate); docidx / ccounts /
+    ratio_csc / eT are the corpus-wide arrays."""
     ld = eT.shape[1]
     _call("ttlda_sstats_csc_block_f64", _p(colptr_block, i64), _p(docidx, i32), _p(ccounts, i32), eT.shape[0], int(V),
           int(K), ld, int(pos_base), int(nnz_block), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats_block, f64),
-          _p(ws), ws.numel() * ws.element_size(), _stream())
+          int(bool(accumulate)), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
 def sstats_fold(sstats_blocks, sstats):

@@ -31,6 +31,7 @@ class DeviceCorpus:
         self.nnz = int(colidx.numel())
         self.tokens = int(counts.sum(dtype=torch.int64).item()) if self.nnz else 0
         self.colptr = self.docidx = self.ccounts = self.csr2csc = None
+        self.serial_blocks = False
         self.nblocks, self.block_docs = 0, 0
         if build_csc:
             self.build_csc()
@@ -64,13 +65,19 @@ class DeviceCorpus:
         import os
 
         ov = os.environ.get("TTLDA_DOC_BLOCKS")
-        if ov:
-            nb = max(1, int(ov))
-        else:
-            row = ld * 8
-            nb = max(1, -(-self.D * row // self.L2_WINDOW_BYTES))
-            if nb > 1 and nb * self.V * row > self.MAX_BLOCK_BYTES:
-                nb = 1  # the window cannot be made L2-sized within the memory cap: stay unblocked (HBM gather)
+        row = ld * 8
+        nb = max(1, int(ov)) if ov else max(1, -(-self.D * row // self.L2_WINDOW_BYTES))
+        # Per-block partial statistics (one launch over all blocks in ticket order, folded afterwards) when they fit the
+        # cap; else unblocked (HBM gather).  TTLDA_SERIAL_BLOCKS=1 selects the buffer-free alternative — one launch per
+        # block accumulating into the final table in place (ttlda_sstats_csc_block_f64, accumulate) — which is exact
+        # and tested but NOT the default for the shapes that would need it: at cfg5 (K = 1000: 191 blocks of 6.5k
+        # documents) a (block, word) segment holds ~13 postings and the per-segment start-up / read-modify-write
+        # epilogue outweighs the L2 residency (587 vs 250 ms for the pass).
+        self.serial_blocks = os.environ.get("TTLDA_SERIAL_BLOCKS", "") == "1"
+        if nb > 1 and not ov and not self.serial_blocks and nb * self.V * row > self.MAX_BLOCK_BYTES:
+            nb = 1
+        if self.serial_blocks and (nb * self.V >= 2 ** 31 or nb * self.V * 8 > self.MAX_BLOCK_BYTES):
+            nb, self.serial_blocks = 1, False
         nb = min(nb, max(1, self.D))
         block_docs = max(1, -(-self.D // nb))
         nb = max(1, -(-self.D // block_docs))
@@ -93,6 +100,9 @@ class DeviceCorpus:
         nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
                       self.colptr, self.docidx, self.ccounts, ws, self.csr2csc if with_map else None)
         self.nblocks, self.block_docs = nblocks, block_docs
+        # mirror position where every block starts (host copy: the per-block entry points take it as an argument)
+        idx = torch.clamp(torch.arange(nblocks + 1, device=dev) * block_docs, max=self.D)
+        self.block_pos = [int(x) for x in self.rowptr[idx].cpu().tolist()]
         self.ccounts_valid = True
         del ws
 

@@ -45,6 +45,7 @@ struct SStatsParams {
     double* carry;       // [nchunks][2][ld]  head / tail partials of words cut by a chunk boundary
     int32_t* carry_word; // [nchunks][2]      virtual word id of each carry slot, -1 = unused
     unsigned long long* ticket;  // next chunk to hand out (zeroed before the launch)
+    int accumulate;              // add to S instead of overwriting it (blocks processed one launch at a time)
 };
 
 // USE_RATIO: the E-step left c/N per posting (ttlda_estep_f64 ratio_csc): the pass is then a pure gather-accumulate
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
                     double a = 0.;
 #pragma unroll
                     for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
+                    if (whole && P.accumulate) a += dst[k];  // serial-block mode: S[w] += this block's partial
                     st_stream_f64(dst + k, a, pol);
                 }
             }
@@ -254,6 +256,7 @@ __global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __gri
                     double a = 0.;
 #pragma unroll
                     for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
+                    if (whole && P.accumulate) a += dst[k];  // serial-block mode: S[w] += this block's partial
                     st_stream_f64(dst + k, a, pol);
                 }
             }
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(256) sstats_carry_kernel(const SStatsParams P)
         for (int k = lane; k < (int)P.ld; k += 32) {
             double s = P.carry[(c * 2 + 1) * P.ld + k];
             for (int64_t c2 = c + 1; c2 <= last; ++c2) s += P.carry[(c2 * 2 + 0) * P.ld + k];
-            P.S[(int64_t)w * P.ld + k] = s;
+            P.S[(int64_t)w * P.ld + k] = P.accumulate ? P.S[(int64_t)w * P.ld + k] + s : s;
         }
     }
 }
@@ -370,7 +373,7 @@ int64_t ttlda_sstats_workspace_bytes(int64_t nnz, int64_t V, int64_t ld, int64_t
 static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const int32_t* ccounts, int64_t D, int64_t V,
                            int64_t K, int64_t ld, int64_t pos_base, int64_t nnz, int64_t nblocks,
                            const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
-                           double* sstats, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+                           double* sstats, int accumulate, void* workspace, int64_t workspace_bytes, cudaStream_t s)
 {
     TTLDA_REQUIRE(colptr && exp_elogtheta && (exp_elogbeta || ratio_csc) && sstats && workspace, "NULL pointer");
     TTLDA_REQUIRE(D >= 0 && V >= 0 && nnz >= 0 && pos_base >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
@@ -394,7 +397,8 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
                      ? (double*)((char*)carry_word + align256((size_t)nc_cap * 2 * sizeof(int32_t)))
                      : sstats;
     const int64_t VV = nblocks * V;
-    cudaError_t e = cudaMemsetAsync(Sb, 0, (size_t)VV * ld * sizeof(double), s);  // words with no postings
+    cudaError_t e = cudaSuccess;
+    if (!accumulate) e = cudaMemsetAsync(Sb, 0, (size_t)VV * ld * sizeof(double), s);  // words with no postings
     if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
     if (nnz == 0 || V == 0) {
         if (nblocks > 1) {
@@ -404,7 +408,7 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
         return TTLDA_OK;
     }
     SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, pos_base, pos_base + nnz, nc, exp_elogtheta, exp_elogbeta,
-                   ratio_csc, Sb, carry, carry_word, ticket};
+                   ratio_csc, Sb, carry, carry_word, ticket, accumulate};
     e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return cuda_fail(e, "memset ticket");
     const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
@@ -454,16 +458,18 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
                          int64_t workspace_bytes, void* stream)
 {
     return sstats_csc_impl(colptr, docidx, ccounts, D, V, K, ld, 0, nnz, nblocks, exp_elogtheta, exp_elogbeta, ratio_csc,
-                           sstats, workspace, workspace_bytes, (cudaStream_t)stream);
+                           sstats, 0, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ttlda_sstats_csc_block_f64(const int64_t* colptr_block, const int32_t* docidx, const int32_t* ccounts, int64_t D,
                                int64_t V, int64_t K, int64_t ld, int64_t pos_base, int64_t nnz_block,
                                const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
-                               double* sstats_block, void* workspace, int64_t workspace_bytes, void* stream)
+                               double* sstats_block, int accumulate, void* workspace, int64_t workspace_bytes,
+                               void* stream)
 {
     return sstats_csc_impl(colptr_block, docidx, ccounts, D, V, K, ld, pos_base, nnz_block, 1, exp_elogtheta,
-                           exp_elogbeta, ratio_csc, sstats_block, workspace, workspace_bytes, (cudaStream_t)stream);
+                           exp_elogbeta, ratio_csc, sstats_block, accumulate != 0, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 
 int ttlda_sstats_fold_f64(const double* sstats_blocks, int64_t nblocks, int64_t V, int64_t ld, double* sstats,

@@ -149,8 +149,9 @@ class LDASmoothed:
         st.ws_s = st.ratio = None
         if self._sstats_mode == "csc":
             corpus.ensure_csc(ld)  # (document-blocked) CSC mirror sized for this K
-            st.ws_s = torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld, corpus.nblocks), dtype=torch.uint8,
-                                  device=dev)
+            st.ws_s = torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld,
+                                                            1 if corpus.serial_blocks else corpus.nblocks),
+                                  dtype=torch.uint8, device=dev)
             if self._ratio_handoff and not self._inner_fixed_point:
                 # c/N per nonzero, written by the E-step in mirror order, consumed by the statistics pass
                 st.ratio = torch.empty(max(corpus.nnz, 1), dtype=f64, device=dev)
@@ -262,6 +263,20 @@ class LDASmoothed:
                      st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
 
+    def _sstats_pass(self, eT, ratio):
+        """The word-major statistics pass over the (blocked) mirror into st.sstats."""
+        st, c = self._st, self._st.corpus
+        if c.serial_blocks and c.nblocks > 1:
+            # one launch per document block, accumulating in place: the launches serialise the blocks, so every block's
+            # theta window is L2-resident without nblocks * V * ld per-block buffers; same bits as the folded form
+            V = st.V
+            for b in range(c.nblocks):
+                s, e = c.block_pos[b], c.block_pos[b + 1]
+                nv.sstats_csc_block(c.colptr[b * V:b * V + V + 1], c.docidx, c.ccounts, V, st.K, s, e - s, eT, st.eB,
+                                    st.sstats, st.ws_s, ratio, accumulate=b > 0)
+        else:
+            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s, ratio)
+
     def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False, online=None):
         """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
         adopt the E-step's gamma / exp(E[log theta]).  have_sstats: st.sstats already holds this rank's statistics
@@ -276,8 +291,7 @@ class LDASmoothed:
         else:
             if not (use_ratio and st.ratio is not None) and not getattr(c, "ccounts_valid", True):
                 c.build_csc(c.nblocks, c.block_docs)  # a streamed step left the mirrored counts stale
-            nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s,
-                          st.ratio if use_ratio else None)
+            self._sstats_pass(eT, st.ratio if use_ratio else None)
         dist = self._dist()
         work = None
         if dist is not None:  # NCCL sum of the K x V statistics over NVLink, asynchronous:
@@ -339,7 +353,7 @@ class LDASmoothed:
             c.csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
         if st.ratio is not None and st.ratio.numel() < max(nnz, 1):
             st.ratio = torch.empty(nnz, dtype=torch.float64, device=dev)
-        need = nv.sstats_workspace_bytes(nnz, V, ld, nb)
+        need = nv.sstats_workspace_bytes(nnz, V, ld, 1 if c.serial_blocks else nb)
         if st.ws_s.numel() < need:
             st.ws_s = torch.empty(need, dtype=torch.uint8, device=dev)
         need = nv.csr_to_csc_workspace_bytes(max_blk, bd, V, 1)
@@ -400,7 +414,8 @@ class LDASmoothed:
         c.ccounts_valid = not use_ratio  # the mirrored counts are not rebuilt when the statistics use the ratios
         # one statistics pass over the whole mirror: its ticket order already walks the blocks one L2 window at a time,
         # and the GPU, not PCIe, bounds this step — per-block passes (ttlda_sstats_csc_block_f64) cost 2.3 ms more
-        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, V, K, nnz, nb, st.eT[cur], st.eB, st.sstats, st.ws_s, st.ratio)
+        c.block_pos = plo
+        self._sstats_pass(st.eT[cur], st.ratio)
         st.part[0].copy_(acc)
         st.iters.copy_(it_acc)
         self.inner_iterations, capped = self._collect(tok_row=0)
