@@ -4,17 +4,19 @@
 // (tuotuo/lda_model.py:262).  The reference scatters K-vectors into a (K,V) matrix document by document; here the
 // same sum is evaluated from the word's side so that the K accumulators of a word live in registers and nothing
 // is scattered:   S[w,k] = sum_{d in postings(w)} eT[d,k] * c_dw / (eT[d,:].eB[w,:] + 1e-100).
-// phi (D x N x K) is never materialised; not even the per-nonzero normaliser is stored — it is recomputed from the
-// gathered eT row (K FMAs), which is cheaper than 12 more bytes per nonzero of HBM traffic.
+// phi (D x N x K) is never materialised.  Two forms: with the ratio c/N of every nonzero left by the E-step in mirror
+// order (USE_RATIO: a pure gather-accumulate, the default), or recomputing the normaliser from the gathered eT row
+// and the word's eB K-vector (callers without the csr->csc map: fixed-point mode).
 //
 // Mapping (traverse.cuh): the word's exp(E[log beta_w]) K-vector is replicated over the warp's R = 32/G lane
 // groups; each group gathers the exp(E[log theta_d]) K-vector of a different posting, R postings per instruction;
 // group partials are summed through shared memory when the word's segment ends.
 //
 // Work decomposition: the nnz CSC positions are cut into fixed chunks (nnz-balanced, immune to Zipfian posting
-// lists); one warp per chunk walks the words intersecting it.  A word that lies wholly inside a chunk is written
-// with a plain store; a word cut by a chunk boundary contributes one partial K-vector per chunk, written to a
-// carry buffer and summed in chunk order by a second kernel => bit-reproducible, no atomics.
+// lists), handed out to warps in mirror order by a ticket counter; a warp walks the words intersecting its chunk.
+// A word that lies wholly inside a chunk is written with a plain store; a word cut by a chunk boundary contributes
+// one partial K-vector per chunk, written to a carry buffer and summed in chunk order by a second kernel =>
+// bit-reproducible, no data atomics (the ticket is the only atomic: it decides WHO computes a chunk, never WHAT).
 //
 // The CSC mirror may be DOCUMENT-BLOCKED (ttlda_csr_to_csc with nblocks > 1): "virtual word" b*V + w holds the
 // postings of word w inside document block b, so that consecutive chunks gather eT rows from one block-sized

@@ -8,14 +8,17 @@ same prints, same attributes (``_lambda_`` (K,V), ``_gamma_`` (M,K), ``_alpha_``
 access.  There is NO CPU path: without a CUDA device / the built library every call raises.
 
 Per EM iteration (tuotuo/lda_model.py:285-316 + :403-409):
-    ttlda_estep_f64        gamma, exp(E[log theta]) refresh, theta-prior term        (e_step :197-270, :142-148)
-                           + the ELBO token term of the INCOMING state (:125-139): it is the same dot product the
-                           E-step normaliser needs, so the perplexity of iteration t is a by-product of E-step t+1
-    [48-byte D2H]          perplexity of the incoming state -> the reference's convergence test (:386-390); the
-                           E-step wrote into ping-pong buffers, so on "converged" it is simply discarded
-    ttlda_sstats_csc_f64   K x V sufficient statistics, word-major, no atomics       (:262)
-    [NCCL all_reduce]      documents are sharded across ranks; sum the statistics    
-    ttlda_mstep_f64        lambda, exp(E[log beta]) refresh, beta-prior term         (:264, m_step :273-283, :157-163)
+    ttlda_estep_f64          gamma (e_step :197-270) + the ELBO token term of the INCOMING state (:125-139): it is the
+                             same dot product the normaliser needs, so the perplexity of iteration t is a by-product
+                             of E-step t+1; leaves the ratio c/N of every nonzero in mirror order for the statistics
+    [48-byte D2H]            perplexity of the incoming state -> the reference's convergence test (:386-390); the
+                             E-step wrote into ping-pong buffers, so on "converged" it is simply discarded
+    ttlda_sstats_csc_f64     K x V sufficient statistics, word-major, no atomics        (:262)
+    [NCCL all_reduce]        documents are sharded across ranks; sum the statistics     
+    ttlda_theta_refresh_f64  exp(E[log theta]) of the new gamma + theta-prior term      (:256, :142-148)
+    ttlda_mstep_f64          lambda, exp(E[log beta]) refresh, beta-prior term          (:264, m_step :273-283, :157-163)
+Beyond the reference: em_step_from_host (one iteration on a corpus streamed from pinned host memory, pipelined per
+document block) and partial_fit (online variational Bayes).
 After the last iteration one ttlda_elbo_tokens_f64 pass yields the final perplexity.
 """
 from __future__ import annotations
