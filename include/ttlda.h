@@ -256,6 +256,11 @@ int ttlda_elbo_tokens_f64(const int64_t* rowptr, const int32_t* colidx, const in
  */
 int ttlda_hyper_stats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* partial_out,
                           void* workspace, int64_t workspace_bytes, void* stream);
+/* Per-column form: out[k] = sum_r (psi(x_rk) - psi(sum_j x_rj)), k < cols — the gradient term of the reference's
+ * non-exchangeable update_alpha, (phsi_gamma - psi(rowsum)).sum(axis=0) at tuotuo/lda_model.py:452-456. */
+int64_t ttlda_hyper_colstats_workspace_bytes(int64_t rows, int64_t cols);
+int ttlda_hyper_colstats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* out,
+                             void* workspace, int64_t workspace_bytes, void* stream);
 int ttlda_psi_f64(const double* x, int64_t n, double* out, void* stream); /* exact digamma, elementwise, x > 0 */
 
 /* layout helpers between the reference's (K,V) topic-major matrices and the word-major device tables */

@@ -80,6 +80,19 @@ def run_fit(X, K, exchangeable=True, D_population=None, **kw):
                 n_warnings=np.int64(len(w)))
 
 
+def run_nonexch_hyper(X, K, newton_steps):
+    """Non-exchangeable update_alpha (lda_model.py:452-456,464-476) — numerically broken upstream (it diverges when run
+    to its 501-step cap), so only its first Newton iterations are pinned."""
+    lda = lda_model.LDASmoothed(num_topics=K, exchangeable_prior=False, verbose=False)
+    lda.fit(DenseCorpus(X), em_num_step=2, update_hyper_parms=False)
+    alpha0 = np.array(lda._alpha_, dtype=np.float64)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        lda.update_alpha(step=newton_steps)
+    return dict(alpha0=alpha0, alpha=np.array(lda._alpha_, dtype=np.float64), gamma=np.array(lda._gamma_),
+                newton_steps=np.int64(newton_steps), n_warnings=np.int64(len(w)))
+
+
 def save(name, **arrays):
     path = os.path.join(HERE, name)
     np.savez_compressed(path, **arrays)
@@ -87,6 +100,10 @@ def save(name, **arrays):
 
 
 def main():
+    if sys.argv[1:] == ["hyper_nonexch"]:  # one fixture only (leaves the other files untouched)
+        X = synth_dense(12, D=120, V=200, K=6, L=40)
+        save("hyper_nonexch.npz", **csr_of(X), K=np.int64(6), **run_nonexch_hyper(X, 6, 3))
+        return
     # ---- A. AS-103 psi / Dirichlet expectation known answers from the compiled reference cutils ------------
     rs = np.random.RandomState(7)
     special = np.array([1e-7, 9.99e-7, 1e-6, 1.0000001e-6, 1e-3, 0.5, 1.0, 2.0, 4.99, 5.0, 5.99, 5.999999, 6.0,
@@ -161,6 +178,9 @@ def main():
     save("fit_nonexch.npz", **csr_of(X), K=np.int64(6),
          kw=json.dumps(dict(em_num_step=4, update_hyper_parms=False)),
          **run_fit(X, 6, exchangeable=False, em_num_step=4, update_hyper_parms=False))
+
+    # ---- D2. non-exchangeable update_alpha, first Newton iterations ------------------------------------------
+    save("hyper_nonexch.npz", **csr_of(X), K=np.int64(6), **run_nonexch_hyper(X, 6, 3))
 
     # ---- E. sampling=True with D_population injected ---------------------------------------------------------
     save("fit_sampling.npz", **csr_of(X), K=np.int64(6), D_population=np.int64(1000),

@@ -644,6 +644,29 @@ def test_partial_fit_online_vs_oracle(K, V):
         m.partial_fit(Document.from_csr(rp, ci, ct, V + 1))
 
 
+def test_nonexchangeable_update_alpha_vs_reference(golden_dir):
+    """update_alpha with a (1,K) array prior: device per-topic digamma statistics (ttlda_hyper_colstats_f64) + the
+    reference's Newton step on the host, against the real reference's first iterations; and fit() now runs through
+    the hyper update with such a prior like the reference does."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+
+    z = np.load(os.path.join(golden_dir, "hyper_nonexch.npz"))
+    V, K = int(z["V"]), int(z["K"])
+    m = LDASmoothed(K, exchangeable_prior=False, verbose=False)
+    m.fit(Document.from_csr(z["rowptr"], z["colidx"], z["counts"], V), em_num_step=2, update_hyper_parms=False)
+    assert relerr(m._gamma_, z["gamma"]) < 1e-9
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m.update_alpha(step=int(z["newton_steps"]))
+    assert len(w) == int(z["n_warnings"])
+    assert m._alpha_.shape == z["alpha"].shape and relerr(m._alpha_, z["alpha"]) < 1e-9
+    o = OracleLDA(K, exchangeable_prior=False)
+    o.fit(CSRCorpus(z["rowptr"], z["colidx"], z["counts"], V), em_num_step=2, update_hyper_parms=False)
+    o.update_alpha(step=int(z["newton_steps"]))
+    assert relerr(m._alpha_, o.alpha) < 1e-10
+
+
 EDGE = [
     # (K, V, rows as lists of (word, count))
     (1, 1, [[(0, 3)]]),                                   # one topic, one word, one document

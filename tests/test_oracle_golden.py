@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py).  CPU only."""
 import json
 import os
+import warnings
 
 import numpy as np
 import pytest
@@ -160,3 +161,22 @@ def test_online_step_reduces_to_batch_step():
     lam1 = a.lam.copy()
     a.partial_fit(X, total_docs=4 * X.D, tau0=1.0, kappa=0.7)  # rho_1 = 2^-0.7: a proper blend
     assert a.t_online == 2 and not np.allclose(a.lam, lam1)
+
+
+def test_nonexchangeable_update_alpha_first_iterations(golden_dir):
+    """The reference's non-exchangeable update_alpha (broken upstream: it diverges at its cap) — its first Newton
+    iterations, pinned against the real reference."""
+    import lda_oracle as orc
+
+    z = np.load(os.path.join(golden_dir, "hyper_nonexch.npz"))
+    X = orc.CSRCorpus(z["rowptr"], z["colidx"], z["counts"], int(z["V"]))
+    o = orc.OracleLDA(int(z["K"]), exchangeable_prior=False)
+    o.fit(X, em_num_step=2, update_hyper_parms=False)
+    assert np.max(np.abs(o.alpha - z["alpha0"])) == 0
+    assert np.max(np.abs(o.gamma - z["gamma"]) / z["gamma"]) < 1e-11
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        o.update_alpha(step=int(z["newton_steps"]))
+    assert len(w) == int(z["n_warnings"])
+    assert o.alpha.shape == z["alpha"].shape
+    assert np.max(np.abs(o.alpha - z["alpha"]) / np.abs(z["alpha"])) < 1e-10

@@ -59,6 +59,8 @@ SIGNATURES = {
     "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
                                              _ptr]),
     "ttlda_hyper_stats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_hyper_colstats_workspace_bytes": (_i64, [_i64, _i64]),
+    "ttlda_hyper_colstats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
     "ttlda_psi_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
     "ttlda_transpose_pad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr]),
     "ttlda_transpose_unpad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
@@ -81,7 +83,7 @@ KERNELS_PER_CALL = {
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
-    "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_psi_f64": 1,
+    "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_hyper_colstats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
 }
 
@@ -310,6 +312,16 @@ def hyper_stats(x, cols, partial, ws):
     rows, ld = x.shape
     _call("ttlda_hyper_stats_f64", _p(x, f64), rows, int(cols), ld, _p(partial, f64), _p(ws),
           ws.numel() * ws.element_size(), _stream())
+
+
+def hyper_colstats(x, cols, out):
+    """out[k] = sum_r (psi(x[r,k]) - psi(sum_j x[r,j])), exact digamma; allocates its own scratch."""
+    rows, ld = x.shape
+    n = int(load().ttlda_hyper_colstats_workspace_bytes(int(rows), int(cols)))
+    if n < 0:
+        _check(n, "ttlda_hyper_colstats_workspace_bytes")
+    ws = torch.empty(n, dtype=torch.uint8, device=x.device)
+    _call("ttlda_hyper_colstats_f64", _p(x, f64), rows, int(cols), ld, _p(out, f64), _p(ws), n, _stream())
 
 
 def psi_exact(x, out):

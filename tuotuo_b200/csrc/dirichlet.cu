@@ -145,6 +145,56 @@ __global__ void __launch_bounds__(256) theta_refresh_kernel(const double* __rest
     }
 }
 
+// ---- per-column exact-digamma statistics: out[k] = sum_r (psi(x_rk) - psi(sum_j x_rj)) --------------------------------
+// (the gradient term of the non-exchangeable update_alpha, lda_model.py:452-456).  One warp per row, lane l owns
+// columns l, l+32, ...; per-CTA partial column sums go to the workspace, hyper_colstats_finish_kernel adds them in CTA
+// order => bit-reproducible.
+constexpr int kColMax = TTLDA_MAX_K / 32;  // columns per lane
+
+__global__ void __launch_bounds__(256) hyper_colstats_kernel(const double* __restrict__ x, int64_t rows, int cols,
+                                                             int64_t ld, double* __restrict__ part)
+{
+    extern __shared__ double sm_col[];  // [warps][cols]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    double acc[kColMax];
+#pragma unroll
+    for (int m = 0; m < kColMax; ++m) acc[m] = 0.;
+    for (int64_t r = warp0; r < rows; r += nwarps) {
+        const double* row = x + r * ld;
+        double s = 0.;
+        for (int k = lane; k < cols; k += 32) s += row[k];
+        const double ps = psi_exact(warp_sum(s));
+#pragma unroll
+        for (int m = 0; m < kColMax; ++m) {
+            const int k = lane + 32 * m;
+            if (k < cols) acc[m] += psi_exact(row[k]) - ps;
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < kColMax; ++m) {
+        const int k = lane + 32 * m;
+        if (k < cols) sm_col[warp * cols + k] = acc[m];
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < cols; k += blockDim.x) {
+        double t = 0.;
+        for (int w = 0; w < nw; ++w) t += sm_col[w * cols + k];
+        part[(int64_t)blockIdx.x * cols + k] = t;
+    }
+}
+
+__global__ void hyper_colstats_finish_kernel(const double* __restrict__ part, int nblocks, int cols,
+                                             double* __restrict__ out)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < cols; k += gridDim.x * blockDim.x) {
+        double t = 0.;
+        for (int b = 0; b < nblocks; ++b) t += part[(int64_t)b * cols + k];
+        out[k] = t;
+    }
+}
+
 // ---- exact-digamma statistics ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) hyper_stats_kernel(const double* __restrict__ x, int64_t rows, int64_t cols,
                                                           int64_t ld, double* __restrict__ records)
@@ -254,6 +304,30 @@ int ttlda_hyper_stats_f64(const double* x, int64_t rows, int64_t cols, int64_t l
     hyper_stats_kernel<<<grid, 256, 0, s>>>(x, rows, cols, ld, (double*)workspace);
     TTLDA_LAUNCH_CHECK("hyper_stats");
     return launch_reduce_records((const double*)workspace, grid, partial_out, s);
+}
+
+int64_t ttlda_hyper_colstats_workspace_bytes(int64_t rows, int64_t cols)
+{
+    if (rows < 0 || cols < 1) return TTLDA_EINVAL;
+    return (int64_t)grid_for_warps(rows, 8, 8) * cols * (int64_t)sizeof(double) + 256;
+}
+
+int ttlda_hyper_colstats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* out, void* workspace,
+                             int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(x && out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(rows >= 0 && cols >= 1 && cols <= TTLDA_MAX_K && ld >= cols, "bad shape");
+    if (workspace_bytes < ttlda_hyper_colstats_workspace_bytes(rows, cols)) {
+        set_error("hyper_colstats: workspace too small");
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = grid_for_warps(rows, 8, 8);
+    hyper_colstats_kernel<<<grid, 256, 8 * cols * sizeof(double), s>>>(x, rows, (int)cols, ld, (double*)workspace);
+    TTLDA_LAUNCH_CHECK("hyper_colstats");
+    hyper_colstats_finish_kernel<<<(int)((cols + 255) / 256), 256, 0, s>>>((const double*)workspace, grid, (int)cols, out);
+    TTLDA_LAUNCH_CHECK("hyper_colstats_finish");
+    return TTLDA_OK;
 }
 
 int ttlda_psi_f64(const double* x, int64_t n, double* out, void* stream)

@@ -641,11 +641,43 @@ class LDASmoothed:
         nv.psi_exact(st.colsum[:st.K].contiguous(), pc)
         return float(st.part[4, 0].item() - st.V * pc.sum().item())
 
+    def _gamma_psi_colstat(self) -> np.ndarray:
+        """(psi(gamma) - psi(rowsum)).sum(axis=0): the K-vector of lda_model.py:452-456 (loop-invariant)."""
+        st = self._st
+        out = torch.empty(st.K, dtype=torch.float64, device=st.dev)
+        nv.hyper_colstats(st.gamma[st.cur], st.K, out)
+        dist = self._dist()
+        if dist is not None:
+            dist.all_reduce(out)
+        return out.cpu().numpy()
+
     def update_alpha(self, step: int = 500, threshold: float = 1e-07, verbose: bool = False) -> None:
         if isinstance(self._alpha_, np.ndarray):
-            # the reference's non-exchangeable branch (lda_model.py:452-456,464-476) diverges
-            raise NotImplementedError("update_alpha for a non-exchangeable prior is numerically broken in the "
-                                      "reference (diverges) and is not reproduced; use update_hyper_parms=False")
+            # Non-exchangeable branch (lda_model.py:452-456,464-476), reproduced AS IS — including `sum_alpha =
+            # alpha * K` (:446, an array, where the sum of alpha was meant), which makes the iteration diverge when it
+            # is run to its cap (SURVEY §8 a9): best effort, the first Newton iterations are pinned by a golden trace.
+            stat = self._gamma_psi_colstat()
+            M, K = self.M, self.K
+            it = 0
+            while it <= step:
+                sum_alpha = self._alpha_ * K  # :446
+                g = M * (psi(sum_alpha) - psi(self._alpha_)) + stat  # :452-456
+                h = -M * polygamma(1, self._alpha_)  # :467
+                z = M * polygamma(1, sum_alpha)  # :470
+                c = np.sum(g / h) / ((1. / z) + np.sum(1. / h))  # :473
+                alpha_new = self._alpha_ - (g - c) / h  # :476, :485
+                delta = np.sum(np.abs(alpha_new - self._alpha_))
+                if verbose:
+                    print(f"M Step: Iteration {it}, Delta Alpha = {delta}")
+                    print(f"Alpha Old:{self._alpha_} -> Alpha New:{alpha_new}")
+                self._alpha_ = alpha_new
+                it += 1
+                if delta < threshold:
+                    self._upload_alpha()
+                    return
+            self._upload_alpha()
+            warnings.warn(f"Update alphda Maximum iteration reached at step {it}")
+            return
         stat = self._gamma_psi_stat()
         M, K = self.M, self.K
         it = 0
