@@ -376,6 +376,89 @@ def test_invariants_at_scale(nv, dev):
     assert st.terms["count"] == c.tokens
 
 
+def test_cfg3_shaped_slice_vs_oracle(monkeypatch, dev):
+    """A slice with the headline configuration's own shape (K=100, V=50k, 300-token documents from the bench's
+    generator) through the production path — blocked mirror, ticket-ordered statistics, ratio hand-off, DMMA group
+    reduction — against the C oracle, hyper update included."""
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import synthetic_document
+
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", "4")
+    doc = synthetic_document("cfg3", device=dev, docs=3000)
+    m = LDASmoothed(100, verbose=False)
+    p = m.fit(doc, em_num_step=3, return_perplexities=True)
+    assert m._st.corpus.nblocks == 4 and m._st.ratio is not None
+    rp, ci, ct = doc.host_csr()
+    o = OracleLDA(100)
+    po = o.fit(CSRCorpus(rp, ci, ct, 50000), em_num_step=3)
+    assert len(p) == len(po) and relerr(p, po) < TOL_PERP
+    assert relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+    assert relerr(m._alpha_, o.alpha) < TOL_STATE and relerr(m._eta_, o.eta) < TOL_STATE
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_corpus_kernels_random_ragged(nv, dev, seed):
+    """bow -> CSR -> (blocked) CSC mirror -> per-block mirror -> widen on random ragged inputs (empty documents, unused
+    vocabulary, long rows), bit-exact against NumPy."""
+    from tuotuo_b200.corpus import DeviceCorpus
+
+    rs = np.random.RandomState(1000 + seed)
+    D, V = int(rs.randint(1, 400)), int(rs.randint(1, 70000 if seed % 2 else 300))
+    lens = rs.poisson(rs.choice([0.5, 5, 60]), size=D)
+    lens[rs.rand(D) < 0.2] = 0
+    tok = rs.randint(0, V, size=int(lens.sum())).astype(np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    c = DeviceCorpus.from_token_ids(torch.as_tensor(tok).to(dev), torch.as_tensor(offs).to(dev), V)
+    rp, ci, ct = c.host_csr()
+    # CSR vs numpy
+    exp_rp, exp_ci, exp_ct = [0], [], []
+    for d in range(D):
+        u, n = np.unique(tok[offs[d]:offs[d + 1]], return_counts=True)
+        exp_ci.append(u)
+        exp_ct.append(n)
+        exp_rp.append(exp_rp[-1] + len(u))
+    exp_ci = np.concatenate(exp_ci) if exp_ci else np.zeros(0)
+    exp_ct = np.concatenate(exp_ct) if exp_ct else np.zeros(0)
+    assert np.array_equal(rp, exp_rp) and np.array_equal(ci, exp_ci) and np.array_equal(ct, exp_ct)
+    nnz = len(ci)
+    # blocked mirror vs numpy (stable sort by (block, word))
+    nb = int(rs.randint(1, 5))
+    bd = max(1, -(-D // nb))
+    nb = max(1, -(-D // bd))
+    c.build_csc(nb, bd)
+    docs = np.repeat(np.arange(D), np.diff(rp))
+    key = (docs // bd) * V + ci
+    order = np.argsort(key, kind="stable")
+    colptr = np.searchsorted(key[order], np.arange(nb * V + 1), side="left")
+    assert np.array_equal(c.colptr.cpu().numpy(), colptr)
+    assert np.array_equal(c.docidx.cpu().numpy()[:nnz], docs[order])
+    assert np.array_equal(c.ccounts.cpu().numpy()[:nnz], ct[order])
+    inv = np.empty(nnz, dtype=np.int64)
+    inv[order] = np.arange(nnz)
+    assert np.array_equal(c.csr2csc.cpu().numpy()[:nnz].astype(np.int64), inv)
+    # the same mirror one block at a time
+    i32 = dict(dtype=torch.int32, device=dev)
+    blk = [torch.full((nb * V + 1,), -1, dtype=torch.int64, device=dev), torch.full((max(nnz, 1),), -1, **i32),
+           torch.full((max(nnz, 1),), -1, **i32), torch.full((max(nnz, 1),), -1, **i32)]
+    ws = torch.empty(nv.csr_to_csc_workspace_bytes(nnz, D, V, 1), dtype=torch.uint8, device=dev)
+    for b in range(nb):
+        d0, d1 = min(b * bd, D), min((b + 1) * bd, D)
+        s, e = int(rp[d0]), int(rp[d1])
+        nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, blk[0][b * V:b * V + V + 1],
+                            blk[1], blk[2], ws, blk[3])
+    assert torch.equal(blk[0], c.colptr)
+    for a, b_ in zip(blk[1:], (c.docidx, c.ccounts, c.csr2csc)):
+        assert torch.equal(a[:nnz], b_[:nnz])
+    # widen
+    if V <= 65536 and nnz:
+        out = torch.empty(nnz, **i32)
+        nv.widen_i32(torch.as_tensor(ci.astype(np.uint16).view(np.int16)).to(dev), out)
+        assert np.array_equal(out.cpu().numpy(), ci)
+        out8 = torch.empty(nnz, **i32)
+        nv.widen_i32(torch.as_tensor(np.minimum(ct, 255).astype(np.uint8)).to(dev), out8)
+        assert np.array_equal(out8.cpu().numpy(), np.minimum(ct, 255))
+
+
 def test_blocked_and_unblocked_statistics_agree(monkeypatch):
     """The document-blocked CSC mirror only reorders the (fixed-order) summation: results agree to rounding."""
     from tuotuo.document import Document
