@@ -150,13 +150,39 @@ __device__ __forceinline__ void walk_rows_carried(const double* __restrict__ tab
 // in-order warp cannot issue past — on the dot -> reduce -> divide -> axpy chain of every sub-batch
 // (tools/membench7.cu: a lone warp's sub-batch drops from 738 to 547 cycles, 12 warps/SM go from 11.8 to 14.2 TB/s).
 // Must be executed by all 32 lanes (mma.sync).
+__device__ __forceinline__ void dmma_8x8x4(double a, double b, double& d0, double& d1)
+{
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
+        : "=d"(d0), "=d"(d1)
+        : "d"(a), "d"(b), "d"(0.0), "d"(0.0));
+}
+
 __device__ __forceinline__ double quad_sum_mma(double p)
 {
     double d0, d1;
-    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%4, %5};"
-        : "=d"(d0), "=d"(d1)
-        : "d"(p), "d"(1.0), "d"(0.0), "d"(0.0));
-    (void)d1;
+    dmma_8x8x4(p, 1.0, d0, d1);
+    return d0;
+}
+
+// Sum over 16 or 32 lanes with three DMMAs and no shuffle at all (a 64-bit shuffle + add step costs an in-order warp
+// ~100 cycles, a DMMA a fraction of that):
+//   1. A = the lanes' values, B = ones            -> every lane holds the sum of its quad (row lane/4 of D)
+//   2. B[k][n] = quad sum held by lane 4n + k, A = selector of k = 0
+//                                                 -> D[i][n] = quad sum n: lane l receives quads 2j, 2j+1 (j = l % 4);
+//                                                    their sum is the sum of lanes 8j .. 8j+7
+//   3. A[i][k] = that 8-lane sum k (masked to the pairs of the row's own group for G = 16), B = ones
+//                                                 -> every lane holds the sum of its group.
+// All additions are exact-order FMAs inside the tensor core: deterministic, identical in every lane of the group.
+template <int G>
+__device__ __forceinline__ double wide_sum_mma(double p, int lane)
+{
+    static_assert(G == 16 || G == 32, "");
+    double d0, d1;
+    dmma_8x8x4(p, 1.0, d0, d1);
+    dmma_8x8x4((lane & 3) == 0 ? 1.0 : 0.0, d0, d0, d1);
+    double s = d0 + d1;  // sum of lanes 8j .. 8j+7, j = lane % 4
+    if (G == 16 && ((lane & 3) >> 1) != (lane >> 4)) s = 0.;
+    dmma_8x8x4(s, 1.0, d0, d1);
     return d0;
 }
 
@@ -164,7 +190,11 @@ __device__ __forceinline__ double quad_sum_mma(double p)
 template <int G>
 __device__ __forceinline__ double group_sum(double p)
 {
-    if constexpr (G >= 4) {
+    if constexpr (G >= 16) {
+        unsigned lane;
+        asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+        return wide_sum_mma<G>(p, (int)lane);
+    } else if constexpr (G >= 4) {
         p = quad_sum_mma(p);
 #pragma unroll
         for (int o = 4; o < G; o <<= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
