@@ -26,7 +26,7 @@
 
 namespace ttlda {
 
-constexpr int kChunk = 512;       // CSC positions per warp work item
+constexpr int kChunk = 1024;      // CSC positions per warp work item
 constexpr int kWordThreads = 128;  // 4 warps per CTA
 
 struct SStatsParams {
