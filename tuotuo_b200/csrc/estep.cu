@@ -193,7 +193,8 @@ __global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel
                 tok_acc += (double)my_c * log(ESTEP ? my_p - 1e-100 : my_p);
                 cnt_acc += (double)my_c;
                 // leave c/N for the statistics pass, in mirror (word-major) order: one scattered 8-byte store
-                if (ESTEP && P.ratio_csc) st_stream_f64(P.ratio_csc + (uint32_t)my_pos, (double)my_c / my_p, pol);
+                if (ESTEP && P.ratio_csc)
+                    st_stream_f64(P.ratio_csc + (uint32_t)my_pos, fast_div_pos((double)my_c, my_p), pol);
             }
         }
 
