@@ -280,7 +280,7 @@ int ttlda_theta_refresh_f64(const double* gamma, int64_t D, int64_t K, int64_t l
     }
     cudaStream_t s = (cudaStream_t)stream;
     const int lpd = K > 256 ? 32 : (K > 128 ? 16 : (K > 32 ? 8 : 4));
-    int grid = grid_for_warps((D + 32 / lpd - 1) / (32 / lpd), 8, 8);
+    int grid = grid_for_warps((D + 32 / lpd - 1) / (32 / lpd), 8, 16);
     double* rec = (double*)workspace;
     if (lpd == 32) theta_refresh_kernel<32><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
     else if (lpd == 16) theta_refresh_kernel<16><<<grid, 256, 0, s>>>(gamma, D, (int)K, ld, alpha_vec, alpha_sum, exp_elogtheta, rec);
