@@ -315,9 +315,15 @@ __global__ void __launch_bounds__(kDocThreads, 4) doc_pass_tma_kernel(const __gr
 template <class Kernel>
 static int resident_grid(Kernel kernel, size_t smem, int64_t D)
 {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kDocThreads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
+    static int per_sm = 0;  // one instance per kernel instantiation (Kernel is a distinct function type per shape/mode
+                            // only through the caller's template: the query is repeated when the pointer changes)
+    static Kernel cached = nullptr;
+    if (cached != kernel || per_sm < 1) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, kDocThreads, smem) != cudaSuccess || n < 1) n = 1;
+        per_sm = n;
+        cached = kernel;
+    }
     return grid_for_warps(D, kDocThreads / 32, per_sm);
 }
 
