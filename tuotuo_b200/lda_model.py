@@ -391,6 +391,9 @@ class LDASmoothed:
         acc = torch.zeros(nv.NPART, dtype=torch.float64, device=dev)
         it_acc = torch.zeros(2, dtype=torch.int64, device=dev)
         use_ratio = st.ratio is not None
+        group = int(os.environ.get("TTLDA_ESTEP_GROUP", "0")) or (2 if (stage_ci is not None and stage_ct is not None) else 1)
+        last = max((b for b in range(nb) if dlo[b + 1] > dlo[b]), default=-1)
+        g0 = 0
         for b in range(nb):
             d0, d1, s, e = dlo[b], dlo[b + 1], plo[b], plo[b + 1]
             if d1 <= d0:
@@ -408,11 +411,16 @@ class LDASmoothed:
             colptr_b = c.colptr[b * V:b * V + V + 1]
             nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, colptr_b, c.docidx,
                                 None if use_ratio else c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
-            nv.estep(c.rowptr[d0:d1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
-                     st.eT[cur][d0:d1], st.eB, st.gamma[cur][d0:d1], st.gamma[nxt][d0:d1], None, e_num_step, 1e-05,
-                     st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
-            acc += st.part[0]
-            it_acc += st.iters
+            # E-step over the blocks mirrored since the last launch: every block when the upload paces the step (int32
+            # arrays), `group` blocks at a time when the GPU does (compact formats) — fewer launch tails
+            if (b + 1 - g0) >= group or b == last:
+                e0, e1 = dlo[g0], d1
+                nv.estep(c.rowptr[e0:e1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
+                         st.eT[cur][e0:e1], st.eB, st.gamma[cur][e0:e1], st.gamma[nxt][e0:e1], None, e_num_step, 1e-05,
+                         st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
+                acc += st.part[0]
+                it_acc += st.iters
+                g0 = b + 1
         c.nnz = nnz
         c.ccounts_valid = not use_ratio  # the mirrored counts are not rebuilt when the statistics use the ratios
         # one statistics pass over the whole mirror: its ticket order already walks the blocks one L2 window at a time,
