@@ -443,7 +443,7 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
         return TTLDA_EINVAL;
     }
     TTLDA_LAUNCH_CHECK("sstats_csc");
-    sstats_carry_kernel<<<grid_for_warps(nc, 8, 8), 256, 0, s>>>(P);
+    sstats_carry_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, s>>>(P);  // one chunk per warp: the pass is three dependent round trips per chunk
     TTLDA_LAUNCH_CHECK("sstats_carry");
     if (nblocks > 1) {
         const int64_t total = V * ld;
