@@ -89,20 +89,32 @@ class DeviceCorpus:
         dev = self.device
         nblocks = max(1, int(nblocks))
         block_docs = int(block_docs) if block_docs else max(1, -(-self.D // nblocks))
-        ws = torch.empty(nv.csr_to_csc_workspace_bytes(self.nnz, self.D, self.V, nblocks), dtype=torch.uint8,
-                         device=dev)
         if self.colptr is None or self.colptr.numel() != nblocks * self.V + 1:
             self.colptr = torch.empty(nblocks * self.V + 1, dtype=torch.int64, device=dev)
         if self.docidx is None:
             self.docidx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
             self.ccounts = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
             self.csr2csc = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)  # uint32 bit patterns
-        nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, nblocks, block_docs,
-                      self.colptr, self.docidx, self.ccounts, ws, self.csr2csc if with_map else None)
-        self.nblocks, self.block_docs = nblocks, block_docs
         # mirror position where every block starts (host copy: the per-block entry points take it as an argument)
         idx = torch.clamp(torch.arange(nblocks + 1, device=dev) * block_docs, max=self.D)
         self.block_pos = [int(x) for x in self.rowptr[idx].cpu().tolist()]
+        if nblocks == 1:
+            ws = torch.empty(nv.csr_to_csc_workspace_bytes(self.nnz, self.D, self.V, 1), dtype=torch.uint8, device=dev)
+            nv.csr_to_csc(self.rowptr, self.colidx, self.counts, self.D, self.V, self.nnz, 1, block_docs,
+                          self.colptr, self.docidx, self.ccounts, ws, self.csr2csc if with_map else None)
+        else:
+            # one block at a time: the same mirror (tested bit for bit) with block-sized sort buffers and block-local
+            # random accesses (20 -> 10 ms at cfg3, 4 GB -> 0.3 GB of scratch)
+            V = self.V
+            big = max(self.block_pos[b + 1] - self.block_pos[b] for b in range(nblocks))
+            ws = torch.empty(nv.csr_to_csc_workspace_bytes(big, block_docs, V, 1), dtype=torch.uint8, device=dev)
+            for b in range(nblocks):
+                d0, d1 = min(b * block_docs, self.D), min((b + 1) * block_docs, self.D)
+                s0, s1 = self.block_pos[b], self.block_pos[b + 1]
+                nv.csr_to_csc_block(self.rowptr[d0:d1 + 1], self.colidx, self.counts, V, d0, s0, s1 - s0,
+                                    self.colptr[b * V:b * V + V + 1], self.docidx, self.ccounts, ws,
+                                    self.csr2csc if with_map else None)
+        self.nblocks, self.block_docs = nblocks, block_docs
         self.ccounts_valid = True
         del ws
 
