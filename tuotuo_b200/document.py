@@ -37,20 +37,19 @@ class Document:
             print(f"On average estimated document length is {round(length / len(sample_docs), 1)} "
                   f"words per document after processing")
 
-        # get_vocab_from_docs + get_np_wct: ids by first appearance (utils.py:177-206)
-        vocab: dict = {}
-        ids = np.empty(length, dtype=np.int32)
+        # get_vocab_from_docs + get_np_wct: ids by first appearance scanning documents in order, tokens left to right
+        # (utils.py:177-206) — which is exactly pandas.factorize's code assignment, at C speed
+        import pandas as pd
+
         offs = np.zeros(len(docs_list) + 1, dtype=np.int64)
-        n = 0
-        for i, doc in enumerate(docs_list):
-            for w in doc:
-                j = vocab.get(w)
-                if j is None:
-                    j = len(vocab)
-                    vocab[w] = j
-                ids[n] = j
-                n += 1
-            offs[i + 1] = n
+        np.cumsum([len(d) for d in docs_list], out=offs[1:])
+        flat = [w for d in docs_list for w in d]
+        if flat:
+            codes, uniques = pd.factorize(np.asarray(flat, dtype=object), sort=False)
+            ids = codes.astype(np.int32)
+            vocab = {w: j for j, w in enumerate(uniques.tolist())}
+        else:
+            ids, vocab = np.empty(0, dtype=np.int32), {}
         print(f"There are {len(vocab)} unique vocab in the corpus after processing")
 
         self.sample_docs_list = docs_list
