@@ -90,7 +90,22 @@ int ttlda_csr_to_csc(const int64_t* rowptr, const int32_t* colidx, const int32_t
 /* Unsigned 8- or 16-bit items -> int32 (src_bytes_per_item = 1 | 2).  Lets a corpus cross PCIe in a compact form
  * (uint16 word ids when V <= 65536, uint8/uint16 counts: 3 instead of 8 bytes per nonzero) and be widened into the
  * colidx / counts arrays on the device. */
-int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, int64_t n, void* stream);
+int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, int64_t n, int64_t bound,
+                    int32_t* flags, void* stream);
+/* bound > 0 (word ids: bound = V): items >= bound set TTLDA_BAD_COLIDX in *flags and are stored as 0. */
+
+/* Validation of a caller-supplied CSR corpus before it drives device addressing (the reference indexes a dense
+ * M x V matrix, tuotuo/lda_model.py:226-227, where a bad index is a NumPy IndexError; here it would be an
+ * out-of-bounds gather).  Checks: rowptr[0] == pos_base, rowptr monotone, rowptr[D] == pos_base + nnz; 0 <= colidx < V;
+ * counts >= 0.  Violations OR the TTLDA_BAD_* bits into flags[0] (device int32, zeroed by the caller).  sanitize != 0
+ * also rewrites the offending entries (rowptr clamped into range, colidx/counts set to 0) so that kernels already
+ * queued behind this call stay in bounds; the corpus must still be rejected.  rowptr or colidx may be NULL (skipped);
+ * with rowptr == NULL this validates a token-id stream against V. */
+#define TTLDA_BAD_ROWPTR 1
+#define TTLDA_BAD_COLIDX 2
+#define TTLDA_BAD_COUNT 4
+int ttlda_validate_csr(int64_t* rowptr, int64_t D, int64_t pos_base, int32_t* colidx, int32_t* counts, int64_t nnz,
+                       int64_t V, int sanitize, int32_t* flags, void* stream);
 
 /* One document block of a document-blocked mirror, built on its own (streaming ingestion: block b can be mirrored,
  * E-stepped and accumulated while block b+1 is still crossing PCIe).  The block holds documents
@@ -262,6 +277,14 @@ int64_t ttlda_hyper_colstats_workspace_bytes(int64_t rows, int64_t cols);
 int ttlda_hyper_colstats_f64(const double* x, int64_t rows, int64_t cols, int64_t ld, double* out,
                              void* workspace, int64_t workspace_bytes, void* stream);
 int ttlda_psi_f64(const double* x, int64_t n, double* out, void* stream); /* exact digamma, elementwise, x > 0 */
+
+/* Measurement aid (bench.py `roofline.peak`): the row-gather rate this device sustains for `n` rows table[idx[i]][0..ld)
+ * read with the library's own traversal (same lane groups, batching and register double-buffering as the E-step and
+ * the statistics pass) and no arithmetic — the ceiling of the np.dot / np.outer gathers of tuotuo/lda_model.py:242,
+ * 248,262 on this table and this index stream, whether they are served by L2 or by HBM.  0 <= idx[i] < rows is the
+ * caller's responsibility; sink double[1] is never written in practice.  Time it with events around the call. */
+int ttlda_probe_gather_f64(const double* table, int64_t rows, int64_t ld, const int32_t* idx, int64_t n,
+                           double* sink, void* stream);
 
 /* layout helpers between the reference's (K,V) topic-major matrices and the word-major device tables */
 int ttlda_transpose_pad_f64(const double* src, int64_t rows, int64_t cols, double* dst, int64_t dst_ld,

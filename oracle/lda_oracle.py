@@ -413,7 +413,8 @@ class OracleLDA:
         return perplexities
 
     # -- NOT in the reference (readme.md:131-136 roadmap): restates LDASmoothed.partial_fit of the CUDA build ----------
-    def partial_fit(self, X: CSRCorpus, total_docs=None, tau0=1.0, kappa=0.7, e_num_step=100):
+    def partial_fit(self, X: CSRCorpus, total_docs=None, tau0=1.0, kappa=0.7, e_num_step=100, gamma_init=None,
+                    e_threshold=1e-05):
         """Online VB (Hoffman, Blei & Bach 2010, Alg. 2) on one minibatch; returns the minibatch perplexity bound under
         the converged gamma and the topics before the update (document part scaled by total_docs / |B|)."""
         assert self.inner_fixed_point, "online steps solve each document to its fixed point"
@@ -424,10 +425,13 @@ class OracleLDA:
             self.lam = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(np.float64, copy=False)
             self.t_online = 0
         self.M, self.V = D, V
-        self.gamma = np.ascontiguousarray(self.alpha + np.ones((D, K), dtype=np.float64) * V / K)
+        if gamma_init is None:
+            self.gamma = np.ascontiguousarray(self.alpha + np.ones((D, K), dtype=np.float64) * V / K)
+        else:  # e.g. 1.0: scikit-learn's start without random_init (tests/test_sklearn_pin.py)
+            self.gamma = np.full((D, K), float(gamma_init))
         Elogtheta = dirichlet_expectation_2d(self.gamma, self.engine)
         Elogbeta = dirichlet_expectation_2d(self.lam, self.engine)
-        self.gamma, (S, Elogtheta) = self.e_step(X, Elogtheta, Elogbeta, e_num_step)
+        self.gamma, (S, Elogtheta) = self.e_step(X, Elogtheta, Elogbeta, e_num_step, e_threshold)
         self.D_population = total
         perp, _ = self.approx_perplexity(X, True, Elogtheta, Elogbeta)
         rho = (tau0 + self.t_online) ** (-kappa)

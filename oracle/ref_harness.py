@@ -19,10 +19,19 @@ import sys
 import types
 
 REF_ROOT = "/root/reference"
+# on the GPU box /root/reference does not exist: the unmodified modules staged by oracle/build_ref.py are used
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def reference_root():
+    for root in ((STAGED_ROOT,) if os.environ.get("TTLDA_REF_STAGED_ONLY") else (REF_ROOT, STAGED_ROOT)):
+        if os.path.exists(os.path.join(root, "tuotuo", "lda_model.py")):
+            return root
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "tuotuo"))
+    return reference_root() is not None
 
 
 def _install_stubs(stopwords):
@@ -75,8 +84,9 @@ def _install_stubs(stopwords):
 
 def import_reference(stopwords=None):
     """Returns the reference's (lda_model, document, generator, cutils) modules."""
-    if not reference_available():
-        raise RuntimeError("reference not present at /root/reference")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference not present at /root/reference nor staged in oracle/_ref/tuotuo")
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, here)
     from build_ref import build_ref, load_ref_cutils
@@ -84,18 +94,18 @@ def import_reference(stopwords=None):
     build_ref()
     cutils = load_ref_cutils()
     loaded = sys.modules.get("tuotuo")
-    if loaded is not None and not str(getattr(loaded, "__file__", "")).startswith(REF_ROOT):
+    if loaded is not None and not str(getattr(loaded, "__file__", "")).startswith(root):
         raise RuntimeError("the repo's own `tuotuo` shim is already imported in this process")
     if stopwords is None:
         stopwords = ["not", "the", "a", "an", "and", "of"]
     _install_stubs(stopwords)
     sys.modules["tuotuo.cutils"] = cutils
-    sys.path.insert(0, REF_ROOT)
+    sys.path.insert(0, root)
     import tuotuo.lda_model as lda_model  # noqa: E402
     import tuotuo.document as document  # noqa: E402
     import tuotuo.generator as generator  # noqa: E402
 
-    assert lda_model.__file__.startswith(REF_ROOT)
+    assert lda_model.__file__.startswith(root)
     return lda_model, document, generator, cutils
 
 

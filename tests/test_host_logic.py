@@ -141,3 +141,21 @@ def test_uci_bag_of_words_reader(tmp_path):
     (tmp_path / "bad.txt").write_text("1\n2\n2\n1 1 1\n")
     with pytest.raises(ValueError):
         Document.from_uci(tmp_path / "bad.txt")
+
+
+def test_from_csr_rejects_malformed_corpora():
+    """Document.from_csr checks what will drive device addressing: ValueError, as NumPy's IndexError would
+    have been in the reference's dense indexing (tuotuo/lda_model.py:226-227)."""
+    import numpy as np
+    import pytest
+
+    from tuotuo_b200.document import Document
+
+    rp, ci, ct = np.array([0, 2, 2, 5]), np.array([1, 3, 0, 2, 4]), np.array([1, 2, 1, 1, 3])
+    d = Document.from_csr(rp, ci, ct, 5)
+    assert d.M == 3 and d.V == 5
+    for bad in [(np.array([0, 2, 1, 5]), ci, ct), (rp, np.array([1, 3, 0, 2, 5]), ct), (rp, np.array([1, 1, 0, 2, 4]), ct),
+                (rp, ci, -ct), (np.array([1, 2, 2, 5]), ci, ct), (rp, np.array([3, 1, 0, 2, 4]), ct), (rp, ci, ct[:4]),
+                (rp, np.array([1, 3, 0, 2, 2 ** 32 + 1]), ct)]:
+        with pytest.raises(ValueError):
+            Document.from_csr(*bad, 5)

@@ -36,7 +36,8 @@ SIGNATURES = {
                                         _i64, _ptr]),
     "ttlda_csr_to_csc_block": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr,
                                               _ptr, _i64, _ptr]),
-    "ttlda_widen_i32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _ptr]),
+    "ttlda_widen_i32": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _ptr, _ptr]),
+    "ttlda_validate_csr": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _ptr, _i64, _i64, ctypes.c_int, _ptr, _ptr]),
     "ttlda_reduce_workspace_bytes": (_i64, []),
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
@@ -62,6 +63,7 @@ SIGNATURES = {
     "ttlda_hyper_colstats_workspace_bytes": (_i64, [_i64, _i64]),
     "ttlda_hyper_colstats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
     "ttlda_psi_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _ptr]),
+    "ttlda_probe_gather_f64": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr, _ptr]),
     "ttlda_transpose_pad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr]),
     "ttlda_transpose_unpad_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
 }
@@ -79,12 +81,12 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 # hand-written kernels launched by each entry point (CUB sort/RLE passes and memsets are not counted)
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
-    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1,
+    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1, "ttlda_validate_csr": 1,
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_hyper_colstats_f64": 2, "ttlda_psi_f64": 1,
-    "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1,
+    "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1, "ttlda_probe_gather_f64": 1,
 }
 
 
@@ -111,6 +113,19 @@ def _check(rc: int, name: str):
         raise TTLDAError(f"{name} failed ({rc}): {msg}")
 
 
+class _DevPtr(ctypes.c_void_p):
+    """A device pointer that remembers which GPU it lives on (`dev`), so that `_call` can launch there."""
+    dev = -1
+
+
+class _StreamOfCall:
+    """Placeholder for the `stream` argument: `_call` substitutes the current stream OF THE DEVICE THE TENSORS LIVE
+    ON (not of the process's current device)."""
+
+
+_STREAM = _StreamOfCall()
+
+
 def _p(t: torch.Tensor | None, dtype=None):
     if t is None:
         return None
@@ -120,27 +135,39 @@ def _p(t: torch.Tensor | None, dtype=None):
         raise TTLDAError("tensor must be contiguous")
     if dtype is not None and t.dtype != dtype:
         raise TTLDAError(f"expected dtype {dtype}, got {t.dtype}")
-    return ctypes.c_void_p(t.data_ptr())
+    p = _DevPtr(t.data_ptr())
+    p.dev = t.device.index
+    return p
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return _STREAM
 
 
 def _call(name, *args):
+    """One C-ABI call.  The entry points launch on the CURRENT device (kernels, memsets, CUB), so the call is made
+    with the tensors' device current and that device's current stream — `LDASmoothed(K, device="cuda:1")` works
+    whatever `torch.cuda.current_device()` is.  Tensors on different devices are refused."""
     global launch_count, kernel_count
+    devs = {a.dev for a in args if isinstance(a, _DevPtr)}
+    if len(devs) > 1:
+        raise TTLDAError(f"{name}: tensors on different CUDA devices {sorted(devs)}")
+    dev = devs.pop() if devs else torch.cuda.current_device()
     launch_count += 1
     kernel_count += KERNELS_PER_CALL[name]
     fn = getattr(load(), name)
-    if timing is None:
-        _check(fn(*args), name)
-        return
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    rc = fn(*args)
-    e1.record()
-    timing.setdefault(name, []).append((e0, e1))
-    _check(rc, name)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev)
+        args = [ctypes.c_void_p(stream.cuda_stream) if a is _STREAM else a for a in args]
+        if timing is None:
+            _check(fn(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        rc = fn(*args)
+        e1.record(stream)
+        timing.setdefault(name, []).append((e0, e1))
+        _check(rc, name)
 
 
 def ld_for(K: int) -> int:
@@ -205,11 +232,30 @@ def csr_to_csc(rowptr, colidx, counts, D, V, nnz, nblocks, block_docs, colptr, d
           _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
-def widen_i32(src, dst):
-    """uint8 / int16-or-uint16 bit patterns (unsigned) -> int32, elementwise."""
+BAD_ROWPTR, BAD_COLIDX, BAD_COUNT = 1, 2, 4
+
+
+def widen_i32(src, dst, bound=0, flags=None):
+    """uint8 / int16-or-uint16 bit patterns (unsigned) -> int32, elementwise.  bound > 0: items >= bound are stored as 0
+    and reported in flags (int32[1], BAD_COLIDX)."""
     if src.element_size() not in (1, 2) or src.numel() != dst.numel():
         raise TTLDAError("widen_i32: source must hold 1- or 2-byte items, one per destination item")
-    _call("ttlda_widen_i32", _p(src), src.element_size(), _p(dst, i32), src.numel(), _stream())
+    _call("ttlda_widen_i32", _p(src), src.element_size(), _p(dst, i32), src.numel(), int(bound), _p(flags, i32),
+          _stream())
+
+
+def validate_csr(rowptr, colidx, counts, V, flags, pos_base=0, sanitize=False, nnz=None):
+    """OR the BAD_* bits of a CSR corpus (or, with rowptr None, of a token-id stream) into flags (int32[1], device)."""
+    D = rowptr.numel() - 1 if rowptr is not None else 0
+    n = int(nnz) if nnz is not None else (colidx.numel() if colidx is not None else 0)
+    _call("ttlda_validate_csr", _p(rowptr, i64), D, int(pos_base), _p(colidx, i32), _p(counts, i32), n, int(V),
+          int(bool(sanitize)), _p(flags, i32), _stream())
+
+
+def bad_corpus_message(flags: int) -> str:
+    what = [m for b, m in ((BAD_ROWPTR, "rowptr must start at 0, be non-decreasing and end at nnz"),
+                           (BAD_COLIDX, "word ids must lie in [0, V)"), (BAD_COUNT, "counts must be >= 0")) if flags & b]
+    return "malformed corpus: " + "; ".join(what)
 
 
 def csr_to_csc_block(rowptr_block, colidx, counts, V, doc_base, pos_base, nnz_block, colptr_block, docidx, ccounts, ws,
@@ -326,6 +372,12 @@ def hyper_colstats(x, cols, out):
 
 def psi_exact(x, out):
     _call("ttlda_psi_f64", _p(x, f64), x.numel(), _p(out, f64), _stream())
+
+
+def probe_gather(table, idx, sink):
+    """Loads-only gather of table[idx[i], :] with the product traversal (roofline probe, bench.py)."""
+    rows, ld = table.shape
+    _call("ttlda_probe_gather_f64", _p(table, f64), rows, ld, _p(idx, i32), idx.numel(), _p(sink, f64), _stream())
 
 
 def transpose_pad(src, dst):

@@ -49,6 +49,12 @@ class DeviceCorpus:
         """Token-id stream (int32, device) + document offsets (int64[D+1], device) -> CSR via ttlda_bow_to_csr."""
         dev = token_ids.device
         T, D = token_ids.numel(), doc_offsets.numel() - 1
+        # ids outside [0, V) would corrupt the (doc, word) sort keys and every later gather: refuse them here
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        nv.validate_csr(doc_offsets.contiguous(), token_ids.contiguous() if T else None, None, V, flags, nnz=T)
+        bad = int(flags.item())
+        if bad:
+            raise ValueError(nv.bad_corpus_message(bad).replace("rowptr", "doc_offsets").replace("nnz", "len(token_ids)"))
         ws = torch.empty(nv.bow_to_csr_workspace_bytes(T, D, V), dtype=torch.uint8, device=dev)
         rowptr = torch.empty(D + 1, dtype=torch.int64, device=dev)
         colidx = torch.empty(max(T, 1), dtype=torch.int32, device=dev)
@@ -58,6 +64,19 @@ class DeviceCorpus:
         nnz = int(nnz_out.item())
         del ws
         return DeviceCorpus(rowptr, colidx[:nnz].clone(), counts[:nnz].clone(), V, **kw)
+
+    def private_copy(self) -> "DeviceCorpus":
+        """A corpus with its own copies of every device array (same blocking, same mirror).  The streaming step
+        (LDASmoothed.em_step_from_host) overwrites the CSR / mirror buffers it works in; it does so in such a copy, never
+        in the instance `Document.device_corpus()` caches."""
+        c = DeviceCorpus.__new__(DeviceCorpus)
+        c.__dict__.update(self.__dict__)
+        for name in ("rowptr", "colidx", "counts", "colptr", "docidx", "ccounts", "csr2csc"):
+            t = getattr(self, name, None)
+            setattr(c, name, t.clone() if t is not None else None)
+        if getattr(self, "block_pos", None) is not None:
+            c.block_pos = list(self.block_pos)
+        return c
 
     def plan_blocks(self, ld: int):
         """Document blocking of the CSC mirror for K-vector rows of `ld` doubles: blocks whose exp(E[log theta])

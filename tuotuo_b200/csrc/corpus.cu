@@ -99,11 +99,66 @@ __global__ void csc_gather_kernel(const uint32_t* __restrict__ skeys, const uint
 
 // Compact host formats (uint16 word ids when V <= 65536, uint8 / uint16 counts) are widened to the int32 arrays the
 // kernels read right after they land on the device: 3 bytes per nonzero cross PCIe instead of 8.
+// bound > 0: items >= bound are reported in *flags (bit 1) and stored as 0, so that nothing downstream can index out
+// of the [V][ld] tables with them (the check rides on a pass that touches every item anyway).
 template <typename T>
-__global__ void __launch_bounds__(256) widen_kernel(const T* __restrict__ src, int32_t* __restrict__ dst, int64_t n)
+__global__ void __launch_bounds__(256) widen_kernel(const T* __restrict__ src, int32_t* __restrict__ dst, int64_t n,
+                                                    uint32_t bound, int32_t* __restrict__ flags)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = (int32_t)src[i];
+    bool bad = false;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = (uint32_t)src[i];
+        if (bound && v >= bound) {
+            bad = true;
+            v = 0;
+        }
+        dst[i] = (int32_t)v;
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, TTLDA_BAD_COLIDX);
+}
+
+// One pass over a CSR corpus that is about to drive device addressing (gathers of eB + w*ld, eT + d*ld, scatters
+// through rowptr): rowptr must start at pos_base, be monotone and end at pos_base + nnz; word ids must lie in [0, V);
+// counts must be >= 0.  Violations are reported in *flags; with `sanitize` they are also made harmless (rowptr clamped
+// into [pos_base, pos_base + nnz] and made monotone by the clamp of each entry against the endpoints only — enough to
+// keep every [b, e) range inside the arrays —, word ids set to 0), so that a caller that checks the flags AFTER queueing
+// its kernels (the streaming step) cannot have corrupted memory in between.
+__global__ void __launch_bounds__(256) validate_csr_kernel(int64_t* __restrict__ rowptr, int64_t D, int64_t pos_base,
+                                                           int32_t* __restrict__ colidx, int32_t* __restrict__ counts,
+                                                           int64_t nnz, int64_t V, int sanitize,
+                                                           int32_t* __restrict__ flags)
+{
+    int bad = 0;
+    const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, step = (int64_t)gridDim.x * blockDim.x;
+    if (rowptr) {
+        const int64_t lo = pos_base, hi = pos_base + nnz;
+        for (int64_t d = i0; d <= D; d += step) {
+            const int64_t r = rowptr[d];
+            bool b = r < lo || r > hi || (d == 0 && r != lo) || (d == D && r != hi);
+            if (!b && d > 0) {
+                const int64_t q = rowptr[d - 1];
+                b = q > r;
+            }
+            if (b) {
+                bad |= TTLDA_BAD_ROWPTR;
+                if (sanitize && (r < lo || r > hi)) rowptr[d] = r < lo ? lo : hi;
+            }
+        }
+    }
+    if (colidx) {
+        for (int64_t p = i0; p < nnz; p += step) {
+            if ((uint64_t)(int64_t)colidx[p] >= (uint64_t)V) {
+                bad |= TTLDA_BAD_COLIDX;
+                if (sanitize) colidx[p] = 0;
+            }
+            if (counts && counts[p] < 0) {
+                bad |= TTLDA_BAD_COUNT;
+                if (sanitize) counts[p] = 0;
+            }
+        }
+    }
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if (bad && (threadIdx.x & 31) == 0) atomicOr(flags, bad);
 }
 
 struct BowWs {
@@ -284,16 +339,34 @@ int ttlda_csr_to_csc_block(const int64_t* rowptr_block, const int32_t* colidx, c
                            csr2csc ? csr2csc + pos_base : csr2csc, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, int64_t n, void* stream)
+int ttlda_widen_i32(const void* src, int64_t src_bytes_per_item, int32_t* dst, int64_t n, int64_t bound,
+                    int32_t* flags, void* stream)
 {
     TTLDA_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "NULL pointer");
     TTLDA_REQUIRE(src_bytes_per_item == 1 || src_bytes_per_item == 2, "source items must be uint8 or uint16");
+    TTLDA_REQUIRE(bound >= 0 && bound <= 65536 && (bound == 0 || flags), "bound needs a flags word; items are < 65536");
     if (n == 0) return TTLDA_OK;
     if (src_bytes_per_item == 1)
-        widen_kernel<uint8_t><<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, dst, n);
+        widen_kernel<uint8_t><<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)src, dst, n,
+                                                                            (uint32_t)bound, flags);
     else
-        widen_kernel<uint16_t><<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst, n);
+        widen_kernel<uint16_t><<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst, n,
+                                                                             (uint32_t)bound, flags);
     TTLDA_LAUNCH_CHECK("widen");
+    return TTLDA_OK;
+}
+
+int ttlda_validate_csr(int64_t* rowptr, int64_t D, int64_t pos_base, int32_t* colidx, int32_t* counts, int64_t nnz,
+                       int64_t V, int sanitize, int32_t* flags, void* stream)
+{
+    TTLDA_REQUIRE(flags, "NULL flags pointer");
+    TTLDA_REQUIRE(D >= 0 && nnz >= 0 && V >= 0 && pos_base >= 0, "negative size");
+    TTLDA_REQUIRE(nnz == 0 || colidx || rowptr, "nothing to validate");
+    const int64_t n = (rowptr ? D + 1 : 0) > (colidx ? nnz : 0) ? D + 1 : nnz;
+    if (n == 0) return TTLDA_OK;
+    validate_csr_kernel<<<grid_1d(n), 256, 0, (cudaStream_t)stream>>>(rowptr, D, pos_base, colidx, counts, nnz, V,
+                                                                      sanitize, flags);
+    TTLDA_LAUNCH_CHECK("validate_csr");
     return TTLDA_OK;
 }
 

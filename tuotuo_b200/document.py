@@ -84,8 +84,31 @@ class Document:
         return self
 
     @classmethod
+    def from_texts_with_vocab(cls, sample_docs: dict, vocab_to_idx: dict, num_doc_population=None):
+        """Raw texts encoded against an EXISTING vocabulary (word -> id) instead of one built by first appearance:
+        what online learning needs, where every minibatch must index the same lambda rows.  Same text pipeline as the
+        constructor; words outside the vocabulary are dropped (returned count in `.oov_tokens`)."""
+        ids, offs, oov = [], [0], 0
+        for _, v in sample_docs.items():
+            for w in text_pipeline(v).split(" "):
+                j = vocab_to_idx.get(w)
+                if j is None:
+                    oov += 1
+                else:
+                    ids.append(j)
+            offs.append(len(ids))
+        self = cls.from_token_ids(np.asarray(ids, dtype=np.int32), np.asarray(offs, dtype=np.int64), len(vocab_to_idx),
+                                  num_doc_population, {v: k for k, v in vocab_to_idx.items()})
+        self.sample_docs = sample_docs
+        self.oov_tokens = oov
+        return self
+
+    @classmethod
     def from_csr(cls, rowptr, colidx, counts, V, num_doc_population=None, idx_to_vocab=None):
-        """Host CSR (NumPy): rowptr int64[M+1], colidx ascending per row, counts."""
+        """Host CSR (NumPy): rowptr int64[M+1], colidx strictly ascending per row in [0, V), counts >= 0 — what
+        np.nonzero(X[d, :]) / X[d, ids] give the reference (tuotuo/lda_model.py:226-227).  Checked here: these arrays
+        drive device addressing, where a bad index is an out-of-bounds gather instead of NumPy's IndexError."""
+        _validate_host_csr(np.asarray(rowptr), np.asarray(colidx), np.asarray(counts), int(V))
         self = cls._blank(len(rowptr) - 1, V, num_doc_population, idx_to_vocab)
         self._host_csr = (np.ascontiguousarray(rowptr, dtype=np.int64), np.ascontiguousarray(colidx, dtype=np.int32),
                           np.ascontiguousarray(counts, dtype=np.int32))
@@ -220,6 +243,29 @@ class Document:
         import pandas as pd
 
         return pd.DataFrame(data=self.doc_vocab_count_array, columns=[self.idx_to_vocab[i] for i in range(self.V)])
+
+
+def _validate_host_csr(rp, ci, ct, V):
+    if rp.ndim != 1 or ci.ndim != 1 or ct.ndim != 1 or len(rp) < 1:
+        raise ValueError("malformed corpus: rowptr, colidx and counts must be 1-D, rowptr non-empty")
+    if len(ci) != len(ct):
+        raise ValueError("malformed corpus: colidx and counts must have one entry per nonzero")
+    if rp[0] != 0 or rp[-1] != len(ci) or (len(rp) > 1 and bool((rp[1:] < rp[:-1]).any())):
+        raise ValueError("malformed corpus: rowptr must start at 0, be non-decreasing and end at nnz")
+    if len(ci):
+        if ci.min() < 0 or ci.max() >= V:
+            raise ValueError("malformed corpus: word ids must lie in [0, V)")
+        if ct.min() < 0:
+            raise ValueError("malformed corpus: counts must be >= 0")
+        if np.asarray(ct).dtype.kind == "f" and not np.all(ct == np.round(ct)):
+            raise ValueError("malformed corpus: counts must be integers")
+        if len(ci) > 1:
+            desc = ci[1:] <= ci[:-1]
+            if desc.any():  # allowed only where a new row starts
+                starts = np.zeros(len(ci) + 1, dtype=bool)
+                starts[np.asarray(rp[1:-1], dtype=np.int64)] = True
+                if bool((desc & ~starts[1:-1]).any()):
+                    raise ValueError("malformed corpus: word ids must be strictly ascending within a document")
 
 
 class _LazyVocab:

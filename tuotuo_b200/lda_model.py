@@ -24,6 +24,7 @@ After the last iteration one ttlda_elbo_tokens_f64 pass yields the final perplex
 from __future__ import annotations
 
 import os
+import time
 import warnings
 
 import numpy as np
@@ -89,11 +90,14 @@ class LDASmoothed:
     # device plumbing
     # ------------------------------------------------------------------------------------------------------------------
     def _dev(self) -> torch.device:
-        if self._device is None:
-            if not torch.cuda.is_available():
-                raise nv.TTLDAError("LDASmoothed needs a CUDA device (sm_100a); there is no CPU fallback")
-            self._device = torch.device("cuda", torch.cuda.current_device())
-        return torch.device(self._device)
+        if self._device is None and not torch.cuda.is_available():
+            raise nv.TTLDAError("LDASmoothed needs a CUDA device (sm_100a); there is no CPU fallback")
+        dev = torch.device(self._device) if self._device is not None else torch.device("cuda")
+        if dev.type == "cuda" and dev.index is None:
+            # pin "cuda" to the device that is current NOW: every later call launches there (_native._call)
+            dev = torch.device("cuda", torch.cuda.current_device())
+        self._device = dev  # a non-CUDA device is refused by nv.check_device in _alloc_state (no CPU path)
+        return dev
 
     @staticmethod
     def _dist():
@@ -147,6 +151,7 @@ class LDASmoothed:
         st.colsum = torch.zeros(ld, dtype=f64, device=dev)
         st.part = torch.zeros((5, nv.NPART), dtype=f64, device=dev)
         st.iters = torch.zeros(2, dtype=torch.int64, device=dev)
+        st.flags = torch.zeros(1, dtype=torch.int32, device=dev)  # TTLDA_BAD_* bits of a streamed corpus
         st.ws = torch.empty(nv.reduce_workspace_bytes(), dtype=torch.uint8, device=dev)
         st.ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
         st.ws_s = st.ratio = None
@@ -280,10 +285,12 @@ class LDASmoothed:
         else:
             nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, eT, st.eB, st.sstats, st.ws_s, ratio)
 
-    def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False, online=None):
-        """Statistics + M-step (lda_model.py:262-264, :273-283) with the state the speculative E-step read, then
-        adopt the E-step's gamma / exp(E[log theta]).  have_sstats: st.sstats already holds this rank's statistics
-        (the block-pipelined streaming path)."""
+    def _launch_statistics(self, use_ratio: bool = True, have_sstats: bool = False):
+        """Statistics pass (lda_model.py:262) with the state the speculative E-step read, [NCCL sum over the document
+        shards], and the theta refresh of the E-step's gamma.  Writes st.sstats, the ping-pong exp(E[log theta]) buffer
+        and a scratch record only — nothing of the CURRENT state — so it can be queued before the host knows whether the
+        iteration will be kept (the perplexity record is still in flight, `_collect_begin`).  Returns the pending
+        collective (or None).  have_sstats: st.sstats already holds this rank's statistics (the streaming path)."""
         st, c = self._st, self._st.corpus
         # the statistics use the theta the E-step read — or, in fixed-point mode, the refreshed one it produced
         eT = st.eT[st.cur ^ 1] if self._inner_fixed_point else st.eT[st.cur]
@@ -299,15 +306,29 @@ class LDASmoothed:
         work = None
         if dist is not None:  # NCCL sum of the K x V statistics over NVLink, asynchronous:
             work = dist.all_reduce(st.sstats, async_op=True)  # the theta refresh below overlaps it
-        # theta refresh of the state being adopted + its theta-prior ELBO term (kept in part[1][0])
-        if self._inner_fixed_point or self._fused_refresh:
-            st.part[1, 0].copy_(st.part[0, 1])  # the E-step kernel produced both
-        else:
+            if nv.timing is not None:  # bench.py: from issuing the collective to the M-step's start
+                st.ev_ar = torch.cuda.Event(enable_timing=True)
+                st.ev_ar.record()
+        if not (self._inner_fixed_point or self._fused_refresh):
             nxt = st.cur ^ 1
             nv.theta_refresh(st.gamma[nxt], st.K, st.alpha_vec, self._alpha_sum(), st.eT[nxt], st.part[4], st.ws)
+        return work
+
+    def _finish_iteration(self, work=None, online=None):
+        """M-step (lda_model.py:264, m_step :273-283) on the summed statistics, then adopt the E-step's gamma /
+        exp(E[log theta]) and its theta-prior ELBO term."""
+        st = self._st
+        if self._inner_fixed_point or self._fused_refresh:
+            st.part[1, 0].copy_(st.part[0, 1])  # the E-step kernel produced gamma's theta-prior term itself
+        else:
             st.part[1, 0].copy_(st.part[4, 0])
         if work is not None:
             work.wait()
+            if nv.timing is not None and getattr(st, "ev_ar", None) is not None:
+                e1 = torch.cuda.Event(enable_timing=True)
+                e1.record()
+                nv.timing.setdefault("nccl_allreduce_to_mstep", []).append((st.ev_ar, e1))
+                st.ev_ar = None
         if online is None:
             nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
         else:  # (scale, rho): stochastic natural-gradient step on lambda (partial_fit)
@@ -315,6 +336,37 @@ class LDASmoothed:
                             st.part[2], st.ws_m)
         st.cur ^= 1
         self._invalidate()
+
+    def _commit_iteration(self, use_ratio: bool = True, have_sstats: bool = False, online=None):
+        self._finish_iteration(self._launch_statistics(use_ratio, have_sstats), online)
+
+    def em_iteration(self, perplexity_prev=None, threshold: float = 1e-05, sampling: bool = False,
+                     e_num_step: int = 100):
+        """ONE pass of `fit`'s loop body (lda_model.py:384-409) on the fitted corpus: E-step from the current state (which
+        also completes the perplexity OF the current state), the reference's convergence test against
+        `perplexity_prev`, statistics, [all-reduce], M-step.  Returns (perplexity of the incoming state, committed):
+        committed is False when `perplexity_prev - perplexity < threshold` (lda_model.py:386-390) — the state is then
+        left untouched, as the reference returns before its em_step.  `perplexity_prev=None` skips the test (first
+        iteration).  This is the call `bench.py` times as `value`.
+
+        The statistics pass, the all-reduce and the theta refresh are queued BEFORE the host reads the perplexity
+        record: they only write scratch / ping-pong buffers, so a converged iteration simply drops them, and the GPU
+        never waits for the host's decision."""
+        if self._st is None:
+            raise RuntimeError("fit() first (em_num_step=0 initialises the state without iterating)")
+        self._estep_speculative(e_num_step)
+        pending = self._collect_begin(tok_row=0)
+        work = self._launch_statistics()
+        self.inner_iterations, capped = self._collect_end(pending)
+        perplexity = self._perplexity_from_terms(sampling)
+        if perplexity_prev is not None and perplexity_prev - perplexity < threshold:
+            if work is not None:
+                work.wait()  # keep the collective sequence identical on every rank; its result is dropped
+            return perplexity, False
+        if capped:
+            warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
+        self._finish_iteration(work)
+        return perplexity, True
 
     # ------------------------------------------------------------------------------------------------------------------
     # streaming entry point: one EM iteration whose corpus arrives from (pinned) host memory
@@ -335,11 +387,19 @@ class LDASmoothed:
             raise RuntimeError("fit() first (em_num_step=0 initialises the state without iterating)")
         if self._inner_fixed_point or self._sstats_mode != "csc":
             raise NotImplementedError("em_step_from_host supports the default (reference-parity, csc) mode")
-        c = st.corpus
         D = rowptr.numel() - 1
         nnz = int(colidx.numel())
         if D != st.D:
             raise ValueError("the streamed corpus must have the fitted number of documents")
+        if counts.numel() != nnz:
+            raise ValueError("colidx and counts must have one entry per nonzero")
+        if not getattr(st, "owns_corpus", False):
+            # the streamed arrays overwrite the device CSR / mirror: do that in buffers owned by THIS fit state, not in
+            # the DeviceCorpus that Document.device_corpus() caches and hands to later fit() / host_csr() calls
+            st.corpus_src = st.corpus
+            st.corpus = st.corpus.private_copy()
+            st.owns_corpus = True
+        c = st.corpus
         if nnz > c.colidx.numel():
             raise ValueError("the streamed corpus has more nonzeros than the device buffers hold")
         dev, V, K, ld = st.dev, st.V, st.K, st.ld
@@ -348,6 +408,13 @@ class LDASmoothed:
         dlo = [min(b * bd, D) for b in range(nb + 1)]
         dlo[nb] = D
         plo = [int(rp_np[d]) for d in dlo]
+        # The row pointers drive host-side slicing and every launch: they are checked here, before anything is uploaded
+        # (~1 ms per million documents, hidden behind the previous step's theta refresh / M-step still on the GPU).
+        # Word ids in [0, V) and counts >= 0 are checked AND made harmless on the device as they land
+        # (ttlda_widen_i32 / ttlda_validate_csr with sanitize) and reported with the step's one device->host read,
+        # before anything is committed.
+        if plo[0] != 0 or plo[nb] != nnz or (D and bool((rp_np[1:] < rp_np[:-1]).any())):
+            raise ValueError(nv.bad_corpus_message(nv.BAD_ROWPTR))
         max_blk = max((plo[b + 1] - plo[b] for b in range(nb)), default=0)
         # buffers that depend on the streamed corpus' nonzero count
         if c.docidx.numel() < max(nnz, 1):
@@ -363,13 +430,14 @@ class LDASmoothed:
         if getattr(st, "ws_c", None) is None or st.ws_c.numel() < need:
             st.ws_c = torch.empty(need, dtype=torch.uint8, device=dev)
 
-        compute = torch.cuda.current_stream()
+        compute = torch.cuda.current_stream(dev)
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
         cs.wait_stream(compute)  # the previous iteration may still be reading the corpus buffers
         with torch.cuda.stream(cs):
             c.rowptr.copy_(rowptr, non_blocking=True)
+        st.flags.zero_()
         # compact host formats: 2-byte word ids (V <= 65536) and 1- or 2-byte counts, all unsigned, are staged as they
         # are and widened into the int32 arrays on the device (3 instead of 8 bytes per nonzero over PCIe)
         def staged(host, name):
@@ -394,20 +462,29 @@ class LDASmoothed:
         group = int(os.environ.get("TTLDA_ESTEP_GROUP", "0")) or (2 if (stage_ci is not None and stage_ct is not None) else 1)
         last = max((b for b in range(nb) if dlo[b + 1] > dlo[b]), default=-1)
         g0 = 0
+        # every block's upload is queued on the copy stream up front (they depend on nothing but the buffers being free)
+        arrived = {}
+        with torch.cuda.stream(cs):
+            for b in range(nb):
+                s, e = plo[b], plo[b + 1]
+                if dlo[b + 1] <= dlo[b]:
+                    continue
+                (c.colidx if stage_ci is None else stage_ci)[s:e].copy_(colidx[s:e], non_blocking=True)
+                (c.counts if stage_ct is None else stage_ct)[s:e].copy_(counts[s:e], non_blocking=True)
+                arrived[b] = torch.cuda.Event()
+                arrived[b].record(cs)
         for b in range(nb):
             d0, d1, s, e = dlo[b], dlo[b + 1], plo[b], plo[b + 1]
             if d1 <= d0:
                 continue
-            with torch.cuda.stream(cs):
-                (c.colidx if stage_ci is None else stage_ci)[s:e].copy_(colidx[s:e], non_blocking=True)
-                (c.counts if stage_ct is None else stage_ct)[s:e].copy_(counts[s:e], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(cs)
-            compute.wait_event(ev)
-            if stage_ci is not None:
-                nv.widen_i32(stage_ci[s:e], c.colidx[s:e])
+            compute.wait_event(arrived[b])
+            if stage_ci is not None:  # word ids >= V are flagged and zeroed by the widening pass itself
+                nv.widen_i32(stage_ci[s:e], c.colidx[s:e], V if V < 65536 else 0, st.flags)
             if stage_ct is not None:
                 nv.widen_i32(stage_ct[s:e], c.counts[s:e])
+            if stage_ci is None:  # int32 word ids: one validation pass (compact ids are checked while being widened)
+                nv.validate_csr(None, c.colidx[s:e], c.counts[s:e] if stage_ct is None else None, V, st.flags,
+                                sanitize=True, nnz=e - s)
             colptr_b = c.colptr[b * V:b * V + V + 1]
             nv.csr_to_csc_block(c.rowptr[d0:d1 + 1], c.colidx, c.counts, V, d0, s, e - s, colptr_b, c.docidx,
                                 None if use_ratio else c.ccounts, st.ws_c, c.csr2csc if use_ratio else None)
@@ -429,7 +506,13 @@ class LDASmoothed:
         self._sstats_pass(st.eT[cur], st.ratio)
         st.part[0].copy_(acc)
         st.iters.copy_(it_acc)
-        self.inner_iterations, capped = self._collect(tok_row=0)
+        try:
+            self.inner_iterations, capped = self._collect(tok_row=0)
+        except ValueError:
+            # a malformed corpus was streamed in (and sanitised on the device): nothing was committed; go back to the
+            # corpus the model was fitted on rather than keep the sanitised garbage as the state's corpus
+            st.corpus, st.owns_corpus = st.corpus_src, False
+            raise
         perplexity = self._perplexity_from_terms(sampling)
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
@@ -440,7 +523,8 @@ class LDASmoothed:
     # online learning (the reference's roadmap item, readme.md:131-136)
     # ------------------------------------------------------------------------------------------------------------------
     def partial_fit(self, minibatch, total_docs: int = None, tau0: float = 1.0, kappa: float = 0.7,
-                    e_num_step: int = 100, return_perplexity: bool = False):
+                    e_num_step: int = 100, return_perplexity: bool = False, *, gamma_init: float = None,
+                    e_threshold: float = 1e-05):
         """One step of online variational Bayes (Hoffman, Blei & Bach 2010, Algorithm 2) on a minibatch of documents.
 
         E-step: every document's gamma is iterated to its fixed point against the current topics
@@ -453,10 +537,24 @@ class LDASmoothed:
 
         return_perplexity: also return the per-word perplexity bound of the minibatch (document part scaled by D/|B| as
         lda_model.py:152-153,187-188 do) under the converged gamma and the topics BEFORE this update — costs one more
-        token pass and a device->host read; otherwise the call is fully asynchronous and returns None."""
-        if not (0.5 < kappa <= 1.0) or tau0 < 0 or (tau0 == 0 and not hasattr(self, "_online_t")):
+        token pass and a device->host read; otherwise the call is fully asynchronous and returns None.
+
+        gamma_init / e_threshold: start value of every gamma_dk (default alpha + V/K, lda_model.py:364) and the L1
+        tolerance of the per-document loop (default 1e-5, :202).  With gamma_init=1.0, e_threshold = K * mean_change_tol,
+        tau0 = learning_offset + 1 and kappa = learning_decay one call IS one
+        sklearn.decomposition.LatentDirichletAllocation._em_step(batch_update=False) without its random gamma start
+        (tests/test_sklearn_pin.py)."""
+        if not (0.5 < kappa <= 1.0) or tau0 < 0 or tau0 + (getattr(self, "_online_t", None) or 0) <= 0:
             raise ValueError("online LDA needs kappa in (0.5, 1] and tau0 >= 0 (tau0 > 0 for the first step)")
-        doc = self._as_document(minibatch)
+        if isinstance(minibatch, dict) and getattr(getattr(self, "train_doc", None), "vocab_to_idx", None):
+            # raw text: every minibatch must index the SAME lambda rows, so it is encoded against the vocabulary of the
+            # first corpus this model saw (a fresh first-appearance vocabulary per minibatch would silently permute the
+            # word ids whenever the sizes happened to agree)
+            doc = Document.from_texts_with_vocab(minibatch, self.train_doc.vocab_to_idx)
+            if doc.oov_tokens:
+                warnings.warn(f"partial_fit: {doc.oov_tokens} tokens outside the model's vocabulary were dropped")
+        else:
+            doc = self._as_document(minibatch)
         corpus = doc.device_corpus(self._dev())
         dist = self._dist()
         n_mb = corpus.D
@@ -473,7 +571,13 @@ class LDASmoothed:
             raise ValueError("the minibatch vocabulary size differs from the model's")
         if not hasattr(self, "train_doc"):
             self.train_doc = doc
-        first = getattr(self, "_online_t", None) is None or self._st is None
+        if not hasattr(self, "M"):
+            self.M = total  # the population the Newton updates (update_alpha) scale with
+        # topics already on the device — from earlier partial_fit calls OR from a batch fit() — are what is updated;
+        # only a model that has never been fitted starts from the reference's lambda_0
+        first = self._st is None
+        if getattr(self, "_online_t", None) is None:
+            self._online_t = 0
         saved = self._inner_fixed_point
         self._inner_fixed_point = True  # documents are solved to their fixed point, not with the frozen-theta loop
         try:
@@ -484,11 +588,10 @@ class LDASmoothed:
                 lam0 = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(DTYPE, copy=False)
                 nv.transpose_pad(torch.as_tensor(lam0).to(st.dev), st.lam)
                 self._refresh_beta()
-                self._online_t = 0
             st.gamma[st.cur].zero_()  # lda_model.py:364
-            st.gamma[st.cur][:, :K] = st.alpha_vec + float(V) / float(K)
+            st.gamma[st.cur][:, :K] = (st.alpha_vec + float(V) / float(K)) if gamma_init is None else float(gamma_init)
             self._refresh_theta()
-            self._estep_speculative(e_num_step)
+            self._estep_speculative(e_num_step, e_threshold)
             perplexity = None
             if return_perplexity:
                 c, nxt = st.corpus, st.cur ^ 1
@@ -512,19 +615,59 @@ class LDASmoothed:
             self._inner_fixed_point = saved
         return perplexity
 
-    def _collect(self, tok_row: int):
-        """One device->host read of the terms of the CURRENT state's ELBO (summed over ranks when sharded).
-        tok_row = 0: token term / token count from the speculative E-step record; 3: from ttlda_elbo_tokens_f64.
-        The theta-prior and beta-prior terms of the current state are kept in part[1][0] and part[2][0]."""
+    def _collect_begin(self, tok_row: int):
+        """Queue the device->host read of the terms of the CURRENT state's ELBO (summed over ranks when sharded) and
+        return a handle for `_collect_end`.  tok_row = 0: token term / token count from the speculative E-step record;
+        3: from ttlda_elbo_tokens_f64.  The theta-prior and beta-prior terms of the current state are kept in
+        part[1][0] and part[2][0].
+
+        Nothing here blocks the compute stream: the (48-byte) all-reduce over ranks runs on NCCL's stream behind the
+        work queued so far, a side stream waits for it and copies the record into pinned host memory, and the caller
+        keeps launching (statistics pass, theta refresh) before it asks for the result."""
         st = self._st
-        buf = torch.stack([st.part[tok_row, 0], st.part[1, 0], st.part[tok_row, 2],
-                           st.iters[0].to(torch.float64), st.iters[1].to(torch.float64), st.part[2, 0]])
+        flags = st.flags.to(torch.float64)
+        buf = torch.cat([torch.stack([st.part[tok_row, 0], st.part[1, 0], st.part[tok_row, 2],
+                                      st.iters[0].to(torch.float64), st.iters[1].to(torch.float64)]),
+                         flags, st.part[2, 0:1]])  # [tok, theta, count, passes, capped, flags | beta (replicated)]
         dist = self._dist()
-        if dist is not None:
-            dist.all_reduce(buf[:5])  # the beta term (entry 5) is replicated, not sharded
-        h = buf.cpu().numpy()
-        st.terms = dict(tok=float(h[0]), theta=float(h[1]), beta=float(h[5]), count=float(h[2]))
+        work = dist.all_reduce(buf[:6], async_op=True) if dist is not None else None
+        if st.dev.type != "cuda":  # only reachable with the test-only CPU stand-ins (tests/cpu_kernels.py, gloo)
+            if work is not None:
+                work.wait()
+            self._host_terms = buf
+            return None
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=st.dev)
+            self._host_terms = torch.empty(7, dtype=torch.float64).pin_memory()
+        main = torch.cuda.current_stream(st.dev)
+        side = self._side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            if work is not None:
+                work.wait()  # makes the SIDE stream wait for the collective; the compute stream does not
+            self._host_terms.copy_(buf, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(side)
+        buf.record_stream(side)
+        return done
+
+    def _collect_end(self, done):
+        if done is not None:
+            t0 = time.perf_counter()
+            done.synchronize()
+            self.host_wait_s = getattr(self, "host_wait_s", 0.0) + (time.perf_counter() - t0)
+        st = self._st
+        h = self._host_terms.numpy().copy()
+        if int(h[5]):  # summed over ranks: only "some rank saw a malformed corpus" survives the sum
+            st.flags.zero_()
+            raise ValueError(nv.bad_corpus_message(int(h[5]) if self._dist() is None else 7)
+                             + " — the iteration was not committed")
+        st.terms = dict(tok=float(h[0]), theta=float(h[1]), beta=float(h[6]), count=float(h[2]))
         return int(h[3]), int(h[4])
+
+    def _collect(self, tok_row: int):
+        """Blocking form: queue the read and wait for it."""
+        return self._collect_end(self._collect_begin(tok_row))
 
     def _perplexity_from_terms(self, sampling: bool) -> float:
         t = self._st.terms
@@ -591,18 +734,13 @@ class LDASmoothed:
         for it in range(em_num_step):  # lda_model.py:384
             # E-step `it` also completes the perplexity of state `it` (initial perplexity for it == 0, :373-378;
             # perplexity after em_step it-1 otherwise, :403-409)
-            self._estep_speculative(e_num_step)
-            self.inner_iterations, capped = self._collect(tok_row=0)
-            perplexity_orig, perplexity = perplexity, self._perplexity_from_terms(sampling)
+            perplexity, committed = self.em_iteration(perplexity if it > 0 else None, threshold, sampling, e_num_step)
             perplexities.append(np.float64(perplexity))
             if it == 0 and verbose:
                 print(f"Init perplexity = {perplexity}")
-            if it > 0 and perplexity_orig - perplexity < threshold:
-                # :386-390 early return (also skips the hyper-parameter update); the speculative E-step is dropped
+            if not committed:
+                # :386-390 early return (also skips the hyper-parameter update); the speculative work is dropped
                 return perplexities if return_perplexities else None
-            if capped:
-                warnings.warn(f"Estep, Maximum iteration reached at step {e_num_step + 1} for {capped} documents")
-            self._commit_iteration()
         # perplexity of the final state (or the initial one when em_num_step == 0)
         self._tokens()
         self._collect(tok_row=3)
@@ -783,24 +921,33 @@ class LDASmoothed:
 
     def e_step(self, X, expec_log_theta, expec_log_beta, step: int = 100, threshold: float = 1e-05,
                batch: bool = True, verbose: bool = False):
-        """lda_model.py:197-270: returns (gamma, (lambda_update (K,V), Elogtheta))."""
+        """lda_model.py:197-270: returns (gamma, (lambda_update (K,V), Elogtheta)).  With inner_fixed_point=True the
+        per-document loop refreshes exp(E[log theta_d]) every pass (scikit-learn's _update_doc_distribution)."""
         self._check_X(X)
         self._load_elogs(expec_log_theta, expec_log_beta)
         st, c = self._st, self._st.corpus
-        cur, nxt = st.cur, st.cur ^ 1
-        nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
-                 st.gamma[cur], st.gamma[nxt], st.eT[nxt], step, threshold, st.iters, st.part[0], st.ws)
-        c.ensure_csc(st.ld)
-        ws_s = torch.empty(nv.sstats_workspace_bytes(c.nnz, st.V, st.ld, c.nblocks), dtype=torch.uint8, device=st.dev)
-        nv.sstats_csc(c.colptr, c.docidx, c.ccounts, st.V, st.K, c.nnz, c.nblocks, st.eT[cur], st.eB, st.sstats, ws_s)
+        nxt = st.cur ^ 1
+        self._estep_speculative(step, threshold)
+        eT = st.eT[nxt] if self._inner_fixed_point else st.eT[st.cur]
+        if self._sstats_mode == "atomic":
+            nv.sstats_atomic(c.rowptr, c.colidx, c.counts, st.K, st.V, eT, st.eB, st.sstats)
+        else:
+            if st.ratio is None and not getattr(c, "ccounts_valid", True):
+                c.build_csc(c.nblocks, c.block_docs)
+            self._sstats_pass(eT, st.ratio)
         dist = self._dist()
         if dist is not None:
             dist.all_reduce(st.sstats)
         upd = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
         nv.transpose_unpad(st.sstats * st.eB, st.K, upd)  # lda_model.py:264
         st.cur = nxt
+        if not (self._inner_fixed_point or self._fused_refresh):
+            self._refresh_theta()  # the E-step wrote gamma only
+        else:
+            st.part[1, 0].copy_(st.part[0, 1])
         self._invalidate("gamma")
-        capped = int(st.iters[1].item())
+        h = st.iters.cpu()
+        self.inner_iterations, capped = int(h[0]), int(h[1])
         if capped:
             warnings.warn(f"Estep, Maximum iteration reached at step {step + 1} for {capped} documents")
         et = torch.empty_like(st.gamma[st.cur])
