@@ -167,6 +167,32 @@ int ttlda_estep_f64(const int64_t* rowptr, const int32_t* colidx, const int32_t*
                     void* workspace, int64_t workspace_bytes, void* stream);
 
 /*
+ * The E-step with a shared-memory cache of the most frequent words' exp(E[log beta_w]) rows (north_star (2): "the
+ * needed columns of exp(E[log beta]) staged in shared memory").  Same update as ttlda_estep_f64 with
+ * exp_elogtheta_out == NULL (gamma only; run ttlda_theta_refresh_f64 afterwards) — tuotuo/lda_model.py:242,248 and the
+ * token term of :125-139 — on an "E-step stream" of the corpus instead of the plain CSR arrays:
+ *   ttlda_estep_hot_rows(ld)   how many rows of ld doubles the cache holds (0: this row width runs ttlda_estep_f64);
+ *   ttlda_build_estream        slot_of_word int32[V] (cache slot of a word, -1 = not cached; the caller picks the H most
+ *                              frequent words) + CSR (+ csr2csc) -> e_idx / e_cnt / e_pos: within every document the
+ *                              cached words first (stable), e_idx = slot | 0x80000000 for them, the word id otherwise;
+ *                              counts and mirror positions permuted alike.  Integer work, bit-exact, once per corpus.
+ *   ttlda_estep_hot_f64        hot_words int32[H] = the word in each slot.  e_pos / ratio_csc: both or neither, as
+ *                              csr2csc / ratio_csc of ttlda_estep_f64.  gamma differs from ttlda_estep_f64's only by the
+ *                              order in which a document's nonzeros are summed (~1 ulp); bit-reproducible run to run.
+ */
+int64_t ttlda_estep_hot_rows(int64_t ld);
+int ttlda_build_estream(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, const uint32_t* csr2csc,
+                        int64_t D, int64_t V, const int32_t* slot_of_word,
+                        int32_t* e_idx, int32_t* e_cnt, uint32_t* e_pos, void* stream);
+int ttlda_estep_hot_f64(const int64_t* rowptr, const int32_t* e_idx, const int32_t* e_cnt, const uint32_t* e_pos,
+                        const int32_t* hot_words, int64_t H,
+                        int64_t D, int64_t K, int64_t V, int64_t ld, const double* alpha_vec,
+                        const double* exp_elogtheta_in, const double* exp_elogbeta,
+                        const double* gamma_in, double* gamma_out, double* ratio_csc,
+                        int64_t max_iter, double tol, int64_t* iters_out, double* partial_out,
+                        void* workspace, int64_t workspace_bytes, void* stream);
+
+/*
  * OPT-IN E-step with a true per-document fixed point (not the reference's behaviour — SURVEY.md §8f row 1):
  * exp(E[log theta_d]) is refreshed after every gamma_d update inside the reference's loop
  * (`while l1 > tol and it <= max_iter`, tuotuo/lda_model.py:236) instead of being frozen, as in Blei/Hoffman and
@@ -199,6 +225,18 @@ int ttlda_sstats_csc_f64(const int64_t* colptr, const int32_t* docidx, const int
                          const double* exp_elogtheta, const double* exp_elogbeta, const double* ratio_csc,
                          double* sstats,
                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Topic-windowed form of the ratio pass, for tables whose rows are long (K >~ 256): one walk of the whole (blocked)
+ * mirror per window of kw columns (kw a multiple of 16, <= 256), gathering only exp_elogtheta[d][k0 .. k0+kw) — so the
+ * L2 working set of a document block is block_docs * kw * 8 bytes and the per-block partials are nblocks * V * kw
+ * doubles, re-used by every window.  ratio_csc is required (ttlda_estep_f64 leaves it); same (K,V) statistics as
+ * ttlda_sstats_csc_f64 up to summation order (~1 ulp), bit-reproducible run to run.  Replaces tuotuo/lda_model.py:262
+ * like the unwindowed pass. */
+int64_t ttlda_sstats_windowed_workspace_bytes(int64_t nnz, int64_t V, int64_t kw, int64_t nblocks);
+int ttlda_sstats_csc_windowed_f64(const int64_t* colptr, const int32_t* docidx,
+                                  int64_t D, int64_t V, int64_t K, int64_t ld, int64_t nnz, int64_t nblocks, int64_t kw,
+                                  const double* exp_elogtheta, const double* ratio_csc, double* sstats,
+                                  void* workspace, int64_t workspace_bytes, void* stream);
 
 /* The same pass over ONE document block of a blocked mirror (built by ttlda_csr_to_csc_block or a slice of
  * ttlda_csr_to_csc): colptr_block = &colptr[b * V] (absolute offsets), docidx / ccounts / ratio_csc / exp_elogtheta

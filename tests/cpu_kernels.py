@@ -195,7 +195,11 @@ def dirichlet_expectation(a, cols, out_elog=None, out_exp=None):
         _np(out_exp)[:, :cols] = np.exp(E)
 
 
-NAMES = ["check_device", "reduce_workspace_bytes", "mstep_workspace_bytes", "sstats_workspace_bytes",
+def estep_hot_rows(ld):
+    return 0  # no shared-memory row cache in the stand-ins: the driver then runs the plain `estep`
+
+
+NAMES = ["check_device", "estep_hot_rows", "reduce_workspace_bytes", "mstep_workspace_bytes", "sstats_workspace_bytes",
          "csr_to_csc_workspace_bytes", "csr_to_csc", "transpose_pad", "transpose_unpad", "theta_refresh", "beta_refresh",
          "estep", "elbo_tokens", "sstats_csc", "sstats_atomic", "mstep", "hyper_stats", "psi_exact",
          "dirichlet_expectation"]

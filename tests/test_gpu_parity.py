@@ -478,6 +478,55 @@ def test_blocked_and_unblocked_statistics_agree(monkeypatch):
     assert relerr(res["1"][1], res["7"][1]) < 1e-12 and relerr(res["1"][2], res["7"][2]) < 1e-12
 
 
+@pytest.mark.parametrize("K,kw,blocks", [(100, "32", "1"), (100, "32", "3"), (300, "128", "2"), (1000, "128", "4"),
+                                         (1000, "256", "1"), (36, "16", "2")])
+def test_topic_windowed_statistics_vs_oracle(monkeypatch, K, kw, blocks):
+    """ttlda_sstats_csc_windowed_f64 (the form cfg5-class shapes run: one walk of the blocked mirror per window of kw
+    topics): same fit as the unwindowed pass and as the oracle; run-to-run bitwise reproducible."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    V, D, L = 1300, 150, 80
+    rp, ci, ct = numpy_corpus(4000 + K, D, V, min(K, 20), L, ragged=True)
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", blocks)
+    monkeypatch.setenv("TTLDA_KWINDOW", "0")
+    plain = LDASmoothed(K, verbose=False)
+    pp = plain.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, return_perplexities=True)
+    assert plain._st.corpus.kwindow == 0
+    monkeypatch.setenv("TTLDA_KWINDOW", kw)
+    runs = []
+    for _ in range(2):
+        m = LDASmoothed(K, verbose=False)
+        p = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, return_perplexities=True)
+        assert m._st.corpus.kwindow == int(kw) and m._st.corpus.nblocks == int(blocks)
+        runs.append((p, m._gamma_.copy(), m._lambda_.copy()))
+    assert np.array_equal(runs[0][1], runs[1][1]) and np.array_equal(runs[0][2], runs[1][2])
+    assert relerr(runs[0][2], plain._lambda_) < 1e-13 and relerr(runs[0][1], plain._gamma_) < 1e-13
+    o = OracleLDA(K, engine="c")
+    po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=2)
+    assert relerr(runs[0][0], po) < TOL_PERP and relerr(runs[0][0], pp) < 1e-12
+    assert relerr(runs[0][1], o.gamma) < TOL_STATE and relerr(runs[0][2], o.lam) < TOL_STATE
+
+
+def test_cfg5_class_shapes_plan_the_windowed_pass():
+    """The planner picks the windowed pass where rows are long (cfg4: K = 500; cfg5: K = 1000, where whole-row blocks
+    could not be afforded at all) and keeps whole rows at cfg3."""
+    from tuotuo_b200.corpus import DeviceCorpus
+
+    def plan(D, V, ld, ok=True):
+        c = DeviceCorpus.__new__(DeviceCorpus)
+        c.D, c.V = D, V
+        nb, bd = c.plan_blocks(ld, windowed_ok=ok)
+        return c.kwindow, nb, bd
+
+    assert plan(1_250_000, 100_000, 1000) == (128, 25, 50_000)
+    assert plan(1_250_000, 100_000, 1000, ok=False)[:2] == (0, 1)
+    assert plan(1_000_000, 50_000, 100)[:2] == (0, 16)
+    assert plan(300_000, 102_660, 500)[:2] == (128, 6)
+    assert plan(300_000, 102_660, 500, ok=False)[:2] == (0, 23)
+
+
 @pytest.mark.parametrize("G,K", [("2", 30), ("4", 60), ("8", 100), ("16", 100), ("16", 250), ("32", 300)])
 def test_every_group_width_is_exact(monkeypatch, G, K):
     """TTLDA_GROUP forces the lanes-per-K-vector mapping; every width must give the same answer as the oracle."""
@@ -563,6 +612,7 @@ def test_em_step_from_host_equals_resident_iteration(monkeypatch, blocks, handof
     for t in (c.colidx, c.counts, c.docidx, c.ccounts, c.csr2csc, c.colptr):
         t.fill_(-1)
     ps = [m.em_step_from_host(*h) for _ in range(3)]
+    c = m._st.corpus  # the streamed step works in a private copy of the corpus buffers, owned by the fit state
     # block-by-block mirror == one-call blocked mirror (with the ratio hand-off the mirrored counts are not rebuilt)
     got = [c.colptr, c.docidx, c.csr2csc if handoff == "1" else c.ccounts]
     want = [mirror[0], mirror[1], mirror[3] if handoff == "1" else mirror[2]]

@@ -47,7 +47,10 @@ def check(m, o, p, po):
 
 
 def test_cfg2_full_fit_vs_oracle():
-    """BASELINE.json configs[1] at its full size, through Document.from_token_ids (ttlda_bow_to_csr counts on the GPU)."""
+    """BASELINE.json configs[1] at its full size, through Document.from_token_ids (ttlda_bow_to_csr counts on the GPU):
+    default `fit` for 3 EM iterations, then the hyper-parameter step.  On this corpus the reference's Newton step drives
+    eta below zero at its first iteration and raises (tuotuo/lda_model.py:539-540) — the oracle does, so must the GPU
+    build, with alpha updated to the same value before that."""
     from tuotuo.document import Document
     from tuotuo.lda_model import LDASmoothed
 
@@ -55,13 +58,28 @@ def test_cfg2_full_fit_vs_oracle():
     assert X.D == 10_000 and X.tokens == 10_000 * 200
     doc = Document.from_token_ids(tok.numpy(), offs.numpy(), V)
     m = LDASmoothed(K, verbose=False)
-    p = m.fit(doc, em_num_step=3, return_perplexities=True)
+    p = m.fit(doc, em_num_step=3, update_hyper_parms=False, return_perplexities=True)
     rp, ci, ct = doc.host_csr()
     assert np.array_equal(rp, X.rowptr) and np.array_equal(ci, X.colidx) and np.array_equal(ct, X.counts)  # bit-exact
     o = OracleLDA(K, engine="c")
-    po = o.fit(X, em_num_step=3)
+    po = o.fit(X, em_num_step=3, update_hyper_parms=False)
     check(m, o, p, po)
     assert m.inner_iterations == 2 * X.D  # the reference's frozen-theta loop: exactly two passes per document
+    # the hyper-parameter step of the default fit (lda_model.py:414-424)
+    o.update_alpha()
+    m.update_alpha()
+    assert relerr(m._alpha_, o.alpha) < TOL_STATE
+    try:
+        o.update_eta()
+        oracle_raises = False
+    except ValueError:
+        oracle_raises = True
+    if oracle_raises:
+        with pytest.raises(ValueError, match="Dirichlet Parameter become < 0"):
+            m.update_eta()
+    else:
+        m.update_eta()
+    assert relerr(m._eta_, o.eta) < TOL_STATE
 
 
 def test_cfg4_shaped_slice_vs_oracle(monkeypatch):
@@ -222,7 +240,7 @@ def test_partial_fit_keeps_one_vocabulary_and_fitted_topics():
     from tuotuo.generator import doc_generator
     from tuotuo.lda_model import LDASmoothed
 
-    gen = doc_generator(M=60, L=25, topic_prior=[0.3] * 5)
+    gen = doc_generator(M=60, L=25, topic_prior=torch.full((5,), 0.3, dtype=torch.double))
     docs = gen.generate_doc()
     keys = list(docs)
     first = {k: docs[k] for k in keys[:30]}

@@ -42,12 +42,19 @@ SIGNATURES = {
     "ttlda_theta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr, _ptr,
                                        _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_estep_hot_rows": (_i64, [_i64]),
+    "ttlda_build_estream": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _ptr]),
+    "ttlda_estep_hot_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                           _ptr, _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_estep_fixed_point_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _f64, _ptr, _ptr, _ptr,
                                                    _ptr, _ptr, _i64, _f64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_sstats_atomic_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "ttlda_sstats_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
     "ttlda_sstats_csc_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
                                             _ptr, _ptr, _i64, _ptr]),
+    "ttlda_sstats_windowed_workspace_bytes": (_i64, [_i64, _i64, _i64, _i64]),
+    "ttlda_sstats_csc_windowed_f64": (ctypes.c_int, [_ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
+                                                     _ptr, _i64, _ptr]),
     "ttlda_sstats_csc_block_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr,
                                                   _ptr, ctypes.c_int, _ptr, _i64, _ptr]),
     "ttlda_sstats_fold_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr]),
@@ -82,8 +89,8 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
     "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1, "ttlda_validate_csr": 1,
-    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_fixed_point_f64": 2,
-    "ttlda_sstats_csc_f64": 2, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
+    "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_hot_f64": 2, "ttlda_build_estream": 1, "ttlda_estep_fixed_point_f64": 2,
+    "ttlda_sstats_csc_f64": 2, "ttlda_sstats_csc_windowed_f64": 0, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
     "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_hyper_colstats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1, "ttlda_probe_gather_f64": 1,
@@ -281,6 +288,25 @@ def estep(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_i
           ws.numel() * ws.element_size(), _stream())
 
 
+def estep_hot_rows(ld) -> int:
+    return max(0, int(load().ttlda_estep_hot_rows(int(ld))))
+
+
+def build_estream(rowptr, colidx, counts, csr2csc, V, slot_of_word, e_idx, e_cnt, e_pos):
+    _call("ttlda_build_estream", _p(rowptr, i64), _p(colidx, i32), _p(counts, i32), _p(csr2csc, torch.int32),
+          rowptr.numel() - 1, int(V), _p(slot_of_word, i32), _p(e_idx, i32), _p(e_cnt, i32), _p(e_pos, torch.int32),
+          _stream())
+
+
+def estep_hot(rowptr, e_idx, e_cnt, e_pos, hot_words, K, V, alpha_vec, eT_in, eB, gamma_in, gamma_out, ratio_csc,
+              max_iter, tol, iters, partial, ws):
+    D, ld = gamma_out.shape
+    _call("ttlda_estep_hot_f64", _p(rowptr, i64), _p(e_idx, i32), _p(e_cnt, i32), _p(e_pos, torch.int32),
+          _p(hot_words, i32), hot_words.numel(), D, int(K), int(V), ld, _p(alpha_vec, f64), _p(eT_in, f64), _p(eB, f64),
+          _p(gamma_in, f64), _p(gamma_out, f64), _p(ratio_csc, f64), int(max_iter), float(tol), _p(iters, i64),
+          _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
 def estep_fixed_point(rowptr, colidx, counts, K, V, alpha_vec, alpha_sum, eT_in, eB, gamma_in, gamma_out, eT_out,
                       max_iter, tol, iters, partial, ws):
     D, ld = gamma_out.shape
@@ -301,6 +327,23 @@ def sstats_csc(colptr, docidx, ccounts, V, K, nnz, nblocks, eT, eB, sstats, ws, 
     _call("ttlda_sstats_csc_f64", _p(colptr, i64), _p(docidx, i32), _p(ccounts, i32), eT.shape[0], int(V), int(K), ld,
           int(nnz),
           int(nblocks), _p(eT, f64), _p(eB, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
+
+
+def sstats_windowed_workspace_bytes(nnz, V, kw, nblocks=1) -> int:
+    r = int(load().ttlda_sstats_windowed_workspace_bytes(int(nnz), int(V), int(kw), int(nblocks)))
+    if r < 0:
+        _check(r, "ttlda_sstats_windowed_workspace_bytes")
+    return r
+
+
+def sstats_csc_windowed(colptr, docidx, V, K, nnz, nblocks, kw, eT, ratio_csc, sstats, ws):
+    """Statistics from the E-step's ratios, one topic window of `kw` columns at a time (long K-vectors)."""
+    global kernel_count
+    ld = eT.shape[1]
+    kernel_count += -(-ld // int(kw)) * (3 if nblocks > 1 else 2)  # per window: pass + carry (+ fold)
+    _call("ttlda_sstats_csc_windowed_f64", _p(colptr, i64), _p(docidx, i32), eT.shape[0], int(V), int(K), ld, int(nnz),
+          int(nblocks), int(kw), _p(eT, f64), _p(ratio_csc, f64), _p(sstats, f64), _p(ws), ws.numel() * ws.element_size(),
+          _stream())
 
 
 def sstats_csc_block(colptr_block, docidx, ccounts, V, K, pos_base, nnz_block, eT, eB, sstats_block, ws, ratio_csc=None,

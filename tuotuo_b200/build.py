@@ -19,7 +19,7 @@ INCLUDE = os.path.join(ROOT, "include")
 OBJ_DIR = os.path.join(PKG, "_obj")
 LIB_PATH = os.path.join(PKG, "libttlda.so")
 
-SOURCES = ["api.cu", "dirichlet.cu", "corpus.cu", "estep.cu", "estep_fp.cu", "sstats.cu", "mstep.cu", "probe.cu"]
+SOURCES = ["api.cu", "dirichlet.cu", "corpus.cu", "estep.cu", "estep_hot.cu", "estep_fp.cu", "sstats.cu", "mstep.cu", "probe.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

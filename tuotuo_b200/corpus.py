@@ -21,6 +21,8 @@ class DeviceCorpus:
                                  # pass 11.0 ms at 8 blocks (100 MB), 9.1 ms at 12-24 blocks (67-33 MB), DESIGN.md §5
     MAX_BLOCK_BYTES = 12 << 30   # cap on the per-block statistics buffer nblocks * V * ld * 8 (cfg4: 23 x 411 MB; its
                                  # write + fold costs ~3 ms and saves ~23 ms of HBM gathers)
+    K_WINDOW = 128               # topic-window width of the windowed statistics pass (ttlda_sstats_csc_windowed_f64):
+                                 # 1 KB per gathered row, the (G=8, E=8) shape of the traversal
 
     def __init__(self, rowptr, colidx, counts, V: int, *, build_csc: bool = False):
         assert rowptr.dtype == torch.int64 and colidx.dtype == torch.int32 and counts.dtype == torch.int32
@@ -32,6 +34,8 @@ class DeviceCorpus:
         self.tokens = int(counts.sum(dtype=torch.int64).item()) if self.nnz else 0
         self.colptr = self.docidx = self.ccounts = self.csr2csc = None
         self.serial_blocks = False
+        self.kwindow = 0  # > 0: the statistics pass walks the mirror once per window of this many topics
+        self.e_idx = self.e_cnt = self.e_pos = self.hot_words = self.slot_of_word = None  # E-step stream, ensure_estream
         self.nblocks, self.block_docs = 0, 0
         if build_csc:
             self.build_csc()
@@ -71,21 +75,41 @@ class DeviceCorpus:
         in the instance `Document.device_corpus()` caches."""
         c = DeviceCorpus.__new__(DeviceCorpus)
         c.__dict__.update(self.__dict__)
-        for name in ("rowptr", "colidx", "counts", "colptr", "docidx", "ccounts", "csr2csc"):
+        for name in ("rowptr", "colidx", "counts", "colptr", "docidx", "ccounts", "csr2csc", "e_idx", "e_cnt", "e_pos"):
             t = getattr(self, name, None)
             setattr(c, name, t.clone() if t is not None else None)
         if getattr(self, "block_pos", None) is not None:
             c.block_pos = list(self.block_pos)
         return c
 
-    def plan_blocks(self, ld: int):
+    def plan_blocks(self, ld: int, windowed_ok: bool = False):
         """Document blocking of the CSC mirror for K-vector rows of `ld` doubles: blocks whose exp(E[log theta])
-        rows fit an L2-sized window, if that needs few enough blocks to keep the per-block statistics small."""
+        rows fit an L2-sized window, if that needs few enough blocks to keep the per-block statistics small.
+
+        windowed_ok (the statistics will run on the E-step's ratios): when whole-row blocks would need more per-block
+        buffer than the cap allows, or rows are long (K > 256), the pass is planned TOPIC-WINDOWED instead:
+        one walk of the mirror per K_WINDOW columns, so a block's L2 footprint is block_docs * K_WINDOW * 8 bytes and
+        the per-block buffers are nblocks * V * K_WINDOW doubles (cfg5 shard: 25 blocks of 51k documents and 2.6 GB
+        instead of 191 blocks and 153 GB).  TTLDA_KWINDOW=<width> forces it, TTLDA_KWINDOW=0 forbids it."""
         import os
 
         ov = os.environ.get("TTLDA_DOC_BLOCKS")
+        kwo = os.environ.get("TTLDA_KWINDOW")
+        self.kwindow = 0
         row = ld * 8
         nb = max(1, int(ov)) if ov else max(1, -(-self.D * row // self.L2_WINDOW_BYTES))
+        too_big = nb > 1 and nb * self.V * row > self.MAX_BLOCK_BYTES
+        long_rows = nb > 1 and ld > 2 * self.K_WINDOW  # measured: cfg4 (K=500) 21.0 -> 19.1 ms, 9.4 -> 0.6 GB of scratch
+        if windowed_ok and kwo != "0" and (long_rows or (too_big and not ov) or (kwo and int(kwo) > 0)):
+            kw = int(kwo) if kwo and int(kwo) > 0 else self.K_WINDOW
+            if kw < ld:
+                nbw = max(1, int(ov)) if ov else max(1, -(-self.D * kw * 8 // self.L2_WINDOW_BYTES))
+                if nbw * self.V * kw * 8 <= self.MAX_BLOCK_BYTES and nbw * self.V < 2 ** 31:
+                    self.kwindow = kw
+                    self.serial_blocks = False
+                    nbw = min(nbw, max(1, self.D))
+                    block_docs = max(1, -(-self.D // nbw))
+                    return max(1, -(-self.D // block_docs)), block_docs
         # Per-block partial statistics (one launch over all blocks in ticket order, folded afterwards) when they fit the
         # cap; else unblocked (HBM gather).  TTLDA_SERIAL_BLOCKS=1 selects the buffer-free alternative — one launch per
         # block accumulating into the final table in place (ttlda_sstats_csc_block_f64, accumulate) — which is exact
@@ -135,12 +159,43 @@ class DeviceCorpus:
                                     self.csr2csc if with_map else None)
         self.nblocks, self.block_docs = nblocks, block_docs
         self.ccounts_valid = True
+        self.e_idx = self.e_cnt = self.e_pos = self.hot_words = None  # derived from csr2csc: rebuilt on demand
         del ws
 
-    def ensure_csc(self, ld: int):
-        nb, bd = self.plan_blocks(ld)
+    def ensure_csc(self, ld: int, windowed_ok: bool = False):
+        nb, bd = self.plan_blocks(ld, windowed_ok)
         if self.colptr is None or (self.nblocks, self.block_docs) != (nb, bd) or not getattr(self, "ccounts_valid", True):
             self.build_csc(nb, bd)
+
+    def ensure_estream(self, ld: int, with_map: bool = True) -> bool:
+        """The E-step stream of ttlda_estep_hot_f64 for rows of `ld` doubles: the H most frequent words (by number of
+        documents containing them; H = what the shared-memory cache holds) get a cache slot, and within every document
+        the nonzeros of cached words come first.  Derived data like the CSC mirror (12 bytes per nonzero); False when
+        this row width has no cached form."""
+        import os
+
+        # opt-in (TTLDA_HOT=1): same-box A/B at cfg3 — 15.2 ms with the cache against 14.3 ms without (DESIGN.md section 7)
+        H = min(nv.estep_hot_rows(ld), self.V) if os.environ.get("TTLDA_HOT", "0") == "1" else 0
+        if ov := os.environ.get("TTLDA_HOT_ROWS"):
+            H = min(H, max(0, int(ov)))
+        if H <= 0 or self.nnz == 0:
+            return False
+        if self.e_idx is not None and self.hot_words.numel() == H and (self.e_pos is not None) == with_map:
+            return True
+        dev = self.device
+        df = torch.bincount(self.colidx[:self.nnz], minlength=self.V)  # documents per word (rows hold distinct words)
+        top = torch.topk(df, H, sorted=True).indices
+        slot = torch.full((self.V,), -1, dtype=torch.int32, device=dev)
+        slot[top] = torch.arange(H, dtype=torch.int32, device=dev)
+        self.hot_words = top.to(torch.int32).contiguous()
+        self.slot_of_word = slot
+        self.hot_share = float(df[top].sum().item()) / max(self.nnz, 1)  # fraction of the nonzeros served from the cache
+        self.e_idx = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        self.e_cnt = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev)
+        self.e_pos = torch.empty(max(self.nnz, 1), dtype=torch.int32, device=dev) if with_map else None
+        nv.build_estream(self.rowptr, self.colidx, self.counts, self.csr2csc if with_map else None, self.V, slot,
+                         self.e_idx, self.e_cnt, self.e_pos)
+        return True
 
     # -- host views ----------------------------------------------------------------------------------------------------
     def host_csr(self):

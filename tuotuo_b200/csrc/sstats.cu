@@ -36,7 +36,11 @@ struct SStatsParams {
     int64_t V;
     int64_t VV;
     int K;
-    int64_t ld;
+    int64_t ld;        // row stride of eT / eB (doubles)
+    int kw;            // width of the topic window [k0, k0 + kw) this launch accumulates (eT, S, carry already point at
+                       // column k0); kw == ld: the whole K-vector
+    int64_t s_ld;      // row stride of S   (ld when S is the final table, kw for per-block partials of a window)
+    int64_t c_ld;      // row stride of carry
     int64_t pos_base;  // mirror positions [pos_base, pos_end) are processed, cut into nchunks chunks (pos_base != 0:
     int64_t pos_end;   // one document block of a corpus-wide mirror, ttlda_sstats_csc_block_f64)
     int64_t nchunks;
@@ -63,8 +67,8 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
 
     const int lane = threadIdx.x & 31;
     const int g = lane % G, r = lane / G;
-    const int ld = (int)P.ld;
-    const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
+    const int ld = (int)P.ld, kw = P.kw;
+    const bool last_ok = KSlice<G, E>::last_slice_ok(g, kw);
     const uint64_t pol = l2_evict_first_policy();
 
     // Chunks are handed out in mirror order through a global ticket counter, so that the warps resident at any moment
@@ -155,11 +159,11 @@ __global__ void __launch_bounds__(kWordThreads, (E <= 8 ? (USE_RATIO ? 4 : 3) : 
             // head slot: the word was started by an earlier chunk; tail slot: it continues in a later one.
             // A word spanning the entire chunk (neither starts nor ends here) uses the head slot.
             const int slot = (pos != wb) ? 0 : 1;
-            double* dst = whole ? P.S + w * P.ld : P.carry + (c * 2 + slot) * P.ld;
+            double* dst = whole ? P.S + w * P.s_ld : P.carry + (c * 2 + slot) * P.c_ld;
 #pragma unroll
             for (int m = 0; m < MMAX; ++m) {
                 const int k = lane + 32 * m;
-                if (k < ld) {
+                if (k < kw) {
                     double a = 0.;
 #pragma unroll
                     for (int q = 0; q < R; ++q) a += wbuf[q * LDP + k];
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(kWordThreads, 4) sstats_tma_kernel(const __gri
             __syncwarp();
             const bool whole = (pos == wb) && (se == we);
             const int slot = (pos != wb) ? 0 : 1;
-            double* dst = whole ? P.S + w * P.ld : P.carry + (c * 2 + slot) * P.ld;
+            double* dst = whole ? P.S + w * P.s_ld : P.carry + (c * 2 + slot) * P.c_ld;
 #pragma unroll
             for (int m = 0; m < MMAX; ++m) {
                 const int k = lane + 32 * m;
@@ -295,10 +299,10 @@ __global__ void __launch_bounds__(256) sstats_carry_kernel(const SStatsParams P)
         if (w < 0) continue;
         int64_t last = c;
         while (last + 1 < P.nchunks && P.carry_word[(last + 1) * 2 + 0] == w) ++last;
-        for (int k = lane; k < (int)P.ld; k += 32) {
-            double s = P.carry[(c * 2 + 1) * P.ld + k];
-            for (int64_t c2 = c + 1; c2 <= last; ++c2) s += P.carry[(c2 * 2 + 0) * P.ld + k];
-            P.S[(int64_t)w * P.ld + k] = P.accumulate ? P.S[(int64_t)w * P.ld + k] + s : s;
+        for (int k = lane; k < P.kw; k += 32) {
+            double s = P.carry[(c * 2 + 1) * P.c_ld + k];
+            for (int64_t c2 = c + 1; c2 <= last; ++c2) s += P.carry[(c2 * 2 + 0) * P.c_ld + k];
+            P.S[(int64_t)w * P.s_ld + k] = P.accumulate ? P.S[(int64_t)w * P.s_ld + k] + s : s;
         }
     }
 }
@@ -312,6 +316,19 @@ __global__ void __launch_bounds__(256) sstats_fold_kernel(const double* __restri
         double s = 0.;
         for (int b = 0; b < nblocks; ++b) s += Sb[(int64_t)b * total + i];
         S[i] = s;
+    }
+}
+
+// The same for one topic window: S[w][k] (k < kw; S already points at column k0, row stride ld) = sum_b Sb[b*V + w][k],
+// Sb rows kw wide
+__global__ void __launch_bounds__(256) sstats_fold_window_kernel(const double* __restrict__ Sb, int64_t V, int kw,
+                                                                 int64_t ld, int nblocks, double* __restrict__ S)
+{
+    const int64_t total = V * kw;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.;
+        for (int b = 0; b < nblocks; ++b) s += Sb[(int64_t)b * total + i];
+        S[(i / kw) * ld + (i % kw)] = s;
     }
 }
 
@@ -409,8 +426,8 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
         }
         return TTLDA_OK;
     }
-    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, pos_base, pos_base + nnz, nc, exp_elogtheta, exp_elogbeta,
-                   ratio_csc, Sb, carry, carry_word, ticket, accumulate};
+    SStatsParams P{colptr, docidx, ccounts, V, VV, (int)K, ld, (int)ld, ld, ld, pos_base, pos_base + nnz, nc,
+                   exp_elogtheta, exp_elogbeta, ratio_csc, Sb, carry, carry_word, ticket, accumulate};
     e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s);
     if (e != cudaSuccess) return cuda_fail(e, "memset ticket");
     const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
@@ -450,6 +467,96 @@ static int sstats_csc_impl(const int64_t* colptr, const int32_t* docidx, const i
         int fg = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
         sstats_fold_kernel<<<fg, 256, 0, s>>>(Sb, V, ld, (int)nblocks, sstats);
         TTLDA_LAUNCH_CHECK("sstats_fold");
+    }
+    return TTLDA_OK;
+}
+
+int64_t ttlda_sstats_windowed_workspace_bytes(int64_t nnz, int64_t V, int64_t kw, int64_t nblocks)
+{
+    if (nnz < 0 || V < 0 || kw < 4 || kw % 4 || nblocks < 1) return TTLDA_EINVAL;
+    const int64_t nc = nchunks_for(nnz) + 1;
+    // [256: ticket][carry, kw wide][carry_word][per-block partials of ONE window, nblocks > 1 only]
+    size_t b = 256 + align256((size_t)nc * 2 * kw * sizeof(double)) + align256((size_t)nc * 2 * sizeof(int32_t));
+    if (nblocks > 1) b += (size_t)nblocks * V * kw * sizeof(double);
+    return (int64_t)b;
+}
+
+// Topic-windowed form of the ratio pass: the K columns are cut into windows of kw, and the WHOLE mirror is walked once
+// per window, gathering only columns [k0, k0 + kw) of every exp(E[log theta]) row.  What a document block contributes to
+// the L2 working set is then block_docs * kw * 8 bytes instead of block_docs * K * 8: at K = 1000 a 50 MB window holds
+// 51k documents instead of 6.5k, so (block, word) segments stay long and the per-block partial statistics
+// (nblocks * V * kw doubles, re-used by every window) stay small — the two things that made document blocking alone
+// unaffordable at cfg5-class shapes.  The price: docidx and ratio are re-read once per window
+// (12 bytes against kw * 8 gathered).  Chunks, carries and the block fold are per column, so the result is
+// bit-reproducible run to run; against the unwindowed pass it differs only in the order in which a word's postings are
+// dealt to the warp's lane groups (R = 32/G depends on the row width): ~1 ulp.
+int ttlda_sstats_csc_windowed_f64(const int64_t* colptr, const int32_t* docidx, int64_t D, int64_t V, int64_t K,
+                                  int64_t ld, int64_t nnz, int64_t nblocks, int64_t kw, const double* exp_elogtheta,
+                                  const double* ratio_csc, double* sstats, void* workspace, int64_t workspace_bytes,
+                                  void* stream)
+{
+    TTLDA_REQUIRE(colptr && exp_elogtheta && ratio_csc && sstats && workspace, "NULL pointer");
+    TTLDA_REQUIRE(D >= 0 && V >= 0 && nnz >= 0 && K >= 1 && K <= TTLDA_MAX_K, "K must be in [1, 1024]");
+    TTLDA_REQUIRE(ld >= K && ld % 4 == 0 && ld < K + 4, "ld must be K rounded up to a multiple of 4");
+    TTLDA_REQUIRE(kw >= 16 && kw % 16 == 0 && kw <= 256, "window width must be a multiple of 16 in [16, 256]");
+    TTLDA_REQUIRE(nblocks >= 1 && nblocks * V < ((int64_t)1 << 31), "bad nblocks");
+    const int64_t need = ttlda_sstats_windowed_workspace_bytes(nnz, V, kw, nblocks);
+    if (workspace_bytes < need) {
+        set_error("sstats_csc_windowed: workspace %lld < %lld", (long long)workspace_bytes, (long long)need);
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e;
+    if (nnz == 0 || V == 0) {
+        e = cudaMemsetAsync(sstats, 0, (size_t)V * ld * sizeof(double), s);
+        return e == cudaSuccess ? TTLDA_OK : cuda_fail(e, "memset sstats");
+    }
+    const int64_t nc = nchunks_for(nnz), nc_cap = nc + 1;
+    char* ws = (char*)workspace;
+    unsigned long long* ticket = (unsigned long long*)ws;
+    ws += 256;
+    double* carry = (double*)ws;
+    int32_t* carry_word = (int32_t*)(ws + align256((size_t)nc_cap * 2 * kw * sizeof(double)));
+    double* Sb = (double*)((char*)carry_word + align256((size_t)nc_cap * 2 * sizeof(int32_t)));
+    const int64_t VV = nblocks * V;
+    const int grid = grid_for_warps(nc, kWordThreads / 32, 16);
+    if (nblocks == 1) {  // words without postings: zero the final table once
+        e = cudaMemsetAsync(sstats, 0, (size_t)V * ld * sizeof(double), s);
+        if (e != cudaSuccess) return cuda_fail(e, "memset sstats");
+    }
+    for (int64_t k0 = 0; k0 < ld; k0 += kw) {
+        const int64_t w = (ld - k0 < kw) ? ld - k0 : kw;  // a multiple of 4
+        SStatsParams P{colptr, docidx, nullptr, V, VV, (int)K, ld, (int)w,
+                       nblocks > 1 ? w : ld, w, 0, nnz, nc, exp_elogtheta + k0, nullptr, ratio_csc,
+                       nblocks > 1 ? Sb : sstats + k0, carry, carry_word, ticket, 0};
+        e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), s);
+        if (e != cudaSuccess) return cuda_fail(e, "memset ticket");
+        if (nblocks > 1) {
+            e = cudaMemsetAsync(Sb, 0, (size_t)VV * w * sizeof(double), s);
+            if (e != cudaSuccess) return cuda_fail(e, "memset window partials");
+        }
+        const GroupShape gs = group_shape_for(w);
+        bool launched = false;
+#define TTLDA_CASE(GG, EE)                        \
+    if (!launched && gs.G == GG && gs.E == EE) {  \
+        launch_shape<GG, EE>(P, grid, s);         \
+        launched = true;                          \
+    }
+        TTLDA_FOR_EACH_SHAPE(TTLDA_CASE)
+#undef TTLDA_CASE
+        if (!launched) {
+            set_error("no kernel instantiated for window width %lld (G=%d, E=%d)", (long long)w, gs.G, gs.E);
+            return TTLDA_EINVAL;
+        }
+        TTLDA_LAUNCH_CHECK("sstats_csc (window)");
+        sstats_carry_kernel<<<(unsigned)((nc + 7) / 8), 256, 0, s>>>(P);
+        TTLDA_LAUNCH_CHECK("sstats_carry (window)");
+        if (nblocks > 1) {
+            const int64_t total = V * w;
+            int fg = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
+            sstats_fold_window_kernel<<<fg, 256, 0, s>>>(Sb, V, (int)w, ld, (int)nblocks, sstats + k0);
+            TTLDA_LAUNCH_CHECK("sstats_fold (window)");
+        }
     }
     return TTLDA_OK;
 }

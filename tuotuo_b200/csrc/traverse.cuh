@@ -228,4 +228,12 @@ inline GroupShape group_shape_for(int64_t ld)
     X(32, 2) X(32, 3) X(32, 4) X(32, 5) X(32, 6) X(32, 7) X(32, 8) X(32, 9) X(32, 10) X(32, 11) X(32, 12) X(32, 13) X(32, 14) \
     X(32, 15) X(32, 16)
 
+// the shapes with E <= 8 (register double-buffering of rows): every ld <= 512
+#define TTLDA_FOR_EACH_SMALL_SHAPE(X)                                                                \
+    X(2, 1) X(2, 2) X(2, 3) X(2, 4) X(2, 5) X(2, 6) X(2, 7) X(2, 8)                                   \
+    X(4, 5) X(4, 6) X(4, 7) X(4, 8)                                                                   \
+    X(8, 5) X(8, 6) X(8, 7) X(8, 8)                                                                   \
+    X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                                               \
+    X(32, 5) X(32, 6) X(32, 7) X(32, 8)
+
 }  // namespace ttlda

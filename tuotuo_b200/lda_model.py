@@ -156,13 +156,17 @@ class LDASmoothed:
         st.ws_m = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
         st.ws_s = st.ratio = None
         if self._sstats_mode == "csc":
-            corpus.ensure_csc(ld)  # (document-blocked) CSC mirror sized for this K
-            st.ws_s = torch.empty(nv.sstats_workspace_bytes(corpus.nnz, V, ld,
-                                                            1 if corpus.serial_blocks else corpus.nblocks),
-                                  dtype=torch.uint8, device=dev)
-            if self._ratio_handoff and not self._inner_fixed_point:
+            handoff = self._ratio_handoff and not self._inner_fixed_point
+            corpus.ensure_csc(ld, windowed_ok=handoff)  # (document-blocked) CSC mirror sized for this K
+            st.ws_s = torch.empty(self._sstats_ws_bytes(corpus, corpus.nnz, V, ld), dtype=torch.uint8, device=dev)
+            if handoff:
                 # c/N per nonzero, written by the E-step in mirror order, consumed by the statistics pass
                 st.ratio = torch.empty(max(corpus.nnz, 1), dtype=f64, device=dev)
+        # E-step stream with the hot words first (shared-memory row cache); needs the mirror's position map when the
+        # ratios are handed over, so it is built after it
+        st.hot = (not self._inner_fixed_point and not self._fused_refresh
+                  and (st.ratio is not None or self._sstats_mode != "csc" or not self._ratio_handoff)
+                  and corpus.ensure_estream(ld, with_map=st.ratio is not None))
         if topics_from is not None:
             if (topics_from.K, topics_from.V, topics_from.dev) != (K, V, dev):
                 raise ValueError("the minibatch must have the vocabulary size / device of the model being updated")
@@ -265,16 +269,33 @@ class LDASmoothed:
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
                      st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
+        elif getattr(st, "hot", False):
+            # gamma only, with the most frequent words' exp(E[log beta]) rows cached in shared memory
+            nv.estep_hot(c.rowptr, c.e_idx, c.e_cnt, c.e_pos if st.ratio is not None else None, c.hot_words, st.K, st.V,
+                         st.alpha_vec, st.eT[cur], st.eB, st.gamma[cur], st.gamma[nxt], st.ratio, e_num_step,
+                         e_threshold, st.iters, st.part[0], st.ws)
         else:
             # gamma only; the theta refresh (digamma / log-gamma / exp per gamma_dk) runs as its own streaming pass
             nv.estep(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(), st.eT[cur], st.eB,
                      st.gamma[cur], st.gamma[nxt], None, e_num_step, e_threshold, st.iters, st.part[0], st.ws,
                      c.csr2csc if st.ratio is not None else None, st.ratio)
 
+    @staticmethod
+    def _sstats_ws_bytes(c, nnz, V, ld) -> int:
+        if c.kwindow:
+            return max(nv.sstats_windowed_workspace_bytes(nnz, V, c.kwindow, c.nblocks),
+                       nv.sstats_workspace_bytes(nnz, V, ld, 1))  # the recomputing form runs unblocked buffers
+        return nv.sstats_workspace_bytes(nnz, V, ld, 1 if c.serial_blocks else c.nblocks)
+
     def _sstats_pass(self, eT, ratio):
         """The word-major statistics pass over the (blocked) mirror into st.sstats."""
         st, c = self._st, self._st.corpus
-        if c.serial_blocks and c.nblocks > 1:
+        if c.kwindow:
+            if ratio is None:
+                raise nv.TTLDAError("the topic-windowed statistics pass runs on the E-step's ratios")
+            nv.sstats_csc_windowed(c.colptr, c.docidx, st.V, st.K, c.nnz, c.nblocks, c.kwindow, eT, ratio, st.sstats,
+                                   st.ws_s)
+        elif c.serial_blocks and c.nblocks > 1:
             # one launch per document block, accumulating in place: the launches serialise the blocks, so every block's
             # theta window is L2-resident without nblocks * V * ld per-block buffers; same bits as the folded form
             V = st.V
@@ -421,9 +442,14 @@ class LDASmoothed:
             c.docidx = torch.empty(nnz, dtype=torch.int32, device=dev)
             c.ccounts = torch.empty(nnz, dtype=torch.int32, device=dev)
             c.csr2csc = torch.empty(nnz, dtype=torch.int32, device=dev)
+        hot = bool(getattr(st, "hot", False)) and c.e_idx is not None
+        if hot and c.e_idx.numel() < max(nnz, 1):
+            c.e_idx = torch.empty(nnz, dtype=torch.int32, device=dev)
+            c.e_cnt = torch.empty(nnz, dtype=torch.int32, device=dev)
+            c.e_pos = torch.empty(nnz, dtype=torch.int32, device=dev) if c.e_pos is not None else None
         if st.ratio is not None and st.ratio.numel() < max(nnz, 1):
             st.ratio = torch.empty(nnz, dtype=torch.float64, device=dev)
-        need = nv.sstats_workspace_bytes(nnz, V, ld, 1 if c.serial_blocks else nb)
+        need = self._sstats_ws_bytes(c, nnz, V, ld)
         if st.ws_s.numel() < need:
             st.ws_s = torch.empty(need, dtype=torch.uint8, device=dev)
         need = nv.csr_to_csc_workspace_bytes(max_blk, bd, V, 1)
@@ -492,9 +518,16 @@ class LDASmoothed:
             # arrays), `group` blocks at a time when the GPU does (compact formats) — fewer launch tails
             if (b + 1 - g0) >= group or b == last:
                 e0, e1 = dlo[g0], d1
-                nv.estep(c.rowptr[e0:e1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
-                         st.eT[cur][e0:e1], st.eB, st.gamma[cur][e0:e1], st.gamma[nxt][e0:e1], None, e_num_step, 1e-05,
-                         st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
+                if hot:  # same kernel as the resident iteration: hot words (of the FITTED corpus) first, rows cached
+                    nv.build_estream(c.rowptr[e0:e1 + 1], c.colidx, c.counts, c.csr2csc if use_ratio else None, V,
+                                     c.slot_of_word, c.e_idx, c.e_cnt, c.e_pos if use_ratio else None)
+                    nv.estep_hot(c.rowptr[e0:e1 + 1], c.e_idx, c.e_cnt, c.e_pos if use_ratio else None, c.hot_words, K,
+                                 V, st.alpha_vec, st.eT[cur][e0:e1], st.eB, st.gamma[cur][e0:e1], st.gamma[nxt][e0:e1],
+                                 st.ratio if use_ratio else None, e_num_step, 1e-05, st.iters, st.part[0], st.ws)
+                else:
+                    nv.estep(c.rowptr[e0:e1 + 1], c.colidx, c.counts, K, V, st.alpha_vec, self._alpha_sum(),
+                             st.eT[cur][e0:e1], st.eB, st.gamma[cur][e0:e1], st.gamma[nxt][e0:e1], None, e_num_step,
+                             1e-05, st.iters, st.part[0], st.ws, c.csr2csc if use_ratio else None, st.ratio)
                 acc += st.part[0]
                 it_acc += st.iters
                 g0 = b + 1
