@@ -385,13 +385,20 @@ def measure(ctx, name, doc, K, V, steps, warmup, *, sampling=False, e2e=False, f
         nbytes = work.numel() * 8
         res["allreduce"] = {"bytes": nbytes, "ms_alone": round(ar_ms, 4),
                             "bus_GBps": round(2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9, 1),
-                            "in_step_ms": per_kernel.get("nccl_allreduce_to_mstep"),
-                            "note": "in_step_ms = from issuing the all-reduce to the M-step's start (the theta refresh "
-                                    "runs inside that window); ms_alone = the collective by itself"}
+                            "exchange_to_mstep_ms": per_kernel.get("exchange_to_mstep"),
+                            "mstep_mode": st.mstep_mode, "peer_error": getattr(st, "peer_error", None),
+                            "note": "ms_alone = an NCCL all-reduce of a table of this size by itself, for reference; the "
+                                    "iteration itself exchanges the statistics in mode `mstep_mode`: peer = NVLink loads / "
+                                    "stores fused into the sharded M-step kernels (their times are in kernel_ms), nccl = "
+                                    "reduce-scatter + all-gather around them, replicated = all-reduce + full M-step; "
+                                    "exchange_to_mstep_ms = from the end of the statistics pass to the M-step's first "
+                                    "kernel (theta refresh + waiting for the slowest rank)"}
         del work
 
     # ---- roofline of the dominant kernel --------------------------------------------------------------------------------
     ab = algorithmic_bytes(c.nnz, c.D, K, V)
+    ab["ttlda_estep_hot_f64"] = ab["ttlda_estep_f64"]
+    ab["ttlda_sstats_csc_windowed_f64"] = ab["ttlda_sstats_csc_f64"] + c.nnz * 12 * max(0, -(-st.ld // max(c.kwindow, 1)) - 1)
     cb = compulsory_bytes(c.nnz, c.D, K, V, 1 if c.serial_blocks else c.nblocks)
     hbm, hbm_src = measured_peaks()
     hot = {k: v for k, v in per_kernel.items() if k in ab}
@@ -592,9 +599,13 @@ def run_ours(args):
     D, L, K, V, pois = CONFIGS[args.config]
     if args.docs:
         D = args.docs
-    doc = synthetic_document(args.config, device=dev, seed=1234 + rank, docs=D)
-    main = measure(ctx, args.config, doc, K, V, args.steps, args.warmup, e2e=True, fit_check=args.fit_check,
-                   scaling="weak", traffic_key=args.config if not args.docs else None)
+    if args.strong and world > 1:  # the SAME corpus on every rank, cut into contiguous nnz-balanced document shards
+        doc = synthetic_document(args.config, device=dev, seed=1234, docs=D).shard(rank, world)
+    else:
+        doc = synthetic_document(args.config, device=dev, seed=1234 + rank, docs=D)
+    main = measure(ctx, args.config, doc, K, V, args.steps, args.warmup, e2e=not args.no_e2e, fit_check=args.fit_check,
+                   scaling="strong" if args.strong else "weak", traffic_key=args.config if not args.docs else None)
+    main.setdefault("e2e", None)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:  # reported at N=1 only (bench contract)
@@ -651,7 +662,8 @@ def run_ours(args):
 
     if rank == 0:
         line = {"metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong" if args.strong else "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"{args.config}: {main['docs']} docs x ~{L} tokens, K={K}, V={V} "
                                        f"({main['docs'] // world} docs per GPU), batch VI EM iteration",
@@ -692,6 +704,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg4 / cfg5 measurements")
     ap.add_argument("--no-parity", action="store_true", help="skip the N>1 shard-vs-oracle check")
+    ap.add_argument("--strong", action="store_true", help="N>1: shard ONE corpus of the configuration over the ranks")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the streamed (host -> device) measurement")
     ap.add_argument("--no-fit-check", dest="fit_check", action="store_false")
     ap.add_argument("--quick-reference", action="store_true", help="--impl reference: skip the cfg2 prefix run")
     args = ap.parse_args()

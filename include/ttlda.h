@@ -283,6 +283,31 @@ int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t l
                            double* colsum_out, double* partial_out,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/*
+ * Sharded M-step for document-sharded multi-GPU runs: rank r owns rows [w0, w0 + n) of
+ * lambda; what the reference does in `lambda_update *= exp(Elogbeta)` / m_step (tuotuo/lda_model.py:264,273-283) over
+ * the whole (K,V) matrix is done once, split over the ranks, instead of on every rank after an all-reduce.
+ *   phase A  ttlda_mstep_slice_lambda_f64: S[w] = sum_i src_tables[i][src_row0 + (w - w0)] in index order — host array of
+ *            `nsrc` DEVICE pointers: every rank's [V][ld] statistics table mapped through peer memory (nsrc = world,
+ *            src_row0 = w0: the reduce-scatter is fused into the kernel as plain NVLink loads), or one buffer a library
+ *            reduce-scatter filled (nsrc = 1, src_row0 = 0);  lambda[w] = eta + S[w] * exp_elogbeta[w] for the slice;
+ *            colsum_part_out double[ld] = column sums of the slice.
+ *   (the caller exchanges the ranks' colsum parts: `colsum_parts` double[nparts][ld], rank order)
+ *   phase B  ttlda_mstep_slice_beta_f64: colsum = sum of the parts in rank order (identical bits on every rank);
+ *            exp_elogbeta rows of the slice = exp(psi~(lambda) - psi~(colsum)), stored into each of the `ndst` tables of
+ *            dst_tables (host array of device pointers: this rank's table, or all ranks' through peer memory — the
+ *            all-gather fused into the kernel as NVLink stores); partial_out[0] = the slice's share of the beta-prior
+ *            term (+ the colsum-only part iff add_colsum_term, which exactly one rank passes).
+ * Workspace for both: ttlda_mstep_workspace_bytes.  lambda / exp_elogbeta are this rank's full [V][ld] tables.
+ */
+int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, int64_t src_row0, int64_t w0, int64_t n,
+                                 int64_t K, int64_t ld, double eta, const double* exp_elogbeta, double* lambda,
+                                 double* colsum_part_out, void* workspace, int64_t workspace_bytes, void* stream);
+int ttlda_mstep_slice_beta_f64(const double* colsum_parts, int64_t nparts, int64_t w0, int64_t n, int64_t K, int64_t ld,
+                               double eta, const double* lambda, double* const* dst_tables, int64_t ndst,
+                               int add_colsum_term, double* colsum_out, double* partial_out,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 /* beta refresh from an existing lambda (initial state, or after a hyper-parameter update):
  * exp_elogbeta = exp(dirichlet_expectation over the vocabulary of lambda[:,k]) and the beta-prior term.
  * Replaces: _dirichlet_expectation_2d(self._lambda_) at tuotuo/lda_model.py:120 and the term at :157-163. */

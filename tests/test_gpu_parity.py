@@ -509,6 +509,105 @@ def test_topic_windowed_statistics_vs_oracle(monkeypatch, K, kw, blocks):
     assert relerr(runs[0][1], o.gamma) < TOL_STATE and relerr(runs[0][2], o.lam) < TOL_STATE
 
 
+@pytest.mark.parametrize("K,V,D,L,handoff", [(20, 120, 200, 40, "1"), (100, 3000, 250, 120, "1"), (100, 3000, 250, 120, "0"),
+                                              (60, 900, 150, 80, "1"), (250, 1500, 80, 150, "1"), (500, 1200, 40, 200, "1")])
+def test_hot_word_cache_estep_vs_oracle(monkeypatch, K, V, D, L, handoff):
+    """Opt-in E-step with the most frequent words' exp(E[log beta]) rows in shared memory (ttlda_estep_hot_f64 on the
+    stream built by ttlda_build_estream): the stream is a per-document stable partition of the CSR row (checked bit for
+    bit), the fit equals the oracle's, and the streamed step runs the same kernel (bitwise equal to the resident one)."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    monkeypatch.setenv("TTLDA_HOT", "1")
+    monkeypatch.setenv("TTLDA_RATIO_HANDOFF", handoff)
+    monkeypatch.setenv("TTLDA_DOC_BLOCKS", "2")
+    rp, ci, ct = numpy_corpus(7000 + K, D, V, min(K, 20), L, ragged=True)
+    m = LDASmoothed(K, verbose=False)
+    p = m.fit(Document.from_csr(rp, ci, ct, V), em_num_step=3, return_perplexities=True)
+    st, c = m._st, m._st.corpus
+    assert st.hot and c.hot_words is not None
+    H = c.hot_words.numel()
+    assert H == min(V, m._st.corpus.hot_words.numel()) and 0 < c.hot_share <= 1.0
+    # the stream: hot entries (slot | 0x80000000) first, in CSR order, then the cold ones, in CSR order
+    e_idx, e_cnt = c.e_idx.cpu().numpy(), c.e_cnt.cpu().numpy()
+    slot = c.slot_of_word.cpu().numpy()
+    hot_words = c.hot_words.cpu().numpy()
+    for d in (0, 1, D // 2, D - 1):
+        b, e = rp[d], rp[d + 1]
+        w, cnt = ci[b:e], ct[b:e]
+        is_hot = slot[w] >= 0
+        want_idx = np.concatenate([(slot[w[is_hot]].astype(np.int64) | 0x80000000).astype(np.uint32).view(np.int32),
+                                   w[~is_hot]])
+        assert np.array_equal(e_idx[b:e], want_idx) and np.array_equal(e_cnt[b:e], np.concatenate([cnt[is_hot], cnt[~is_hot]]))
+        assert np.array_equal(hot_words[slot[w[is_hot]]], w[is_hot])
+    o = OracleLDA(K, engine="c")
+    po = o.fit(CSRCorpus(rp, ci, ct, V), em_num_step=3)
+    assert relerr(p, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+    assert m.inner_iterations == 2 * D
+    # streamed step == resident iteration, bit for bit, with the cache on both sides
+    a = LDASmoothed(K, verbose=False)
+    a.fit(Document.from_csr(rp, ci, ct, V), em_num_step=2, update_hyper_parms=False)
+    b_ = LDASmoothed(K, verbose=False)
+    b_.fit(Document.from_csr(rp, ci, ct, V), em_num_step=0, update_hyper_parms=False)
+    h = [torch.as_tensor(x).pin_memory() for x in (rp, ci, ct)]
+    for _ in range(2):
+        b_.em_step_from_host(*h)
+    assert np.array_equal(a._gamma_, b_._gamma_) and np.array_equal(a._lambda_, b_._lambda_)
+
+
+@pytest.mark.parametrize("K,V,N", [(20, 97, 3), (100, 1000, 8), (500, 333, 2), (7, 5, 8)])
+def test_sharded_mstep_slices_equal_full_mstep(nv, dev, K, V, N):
+    """ttlda_mstep_slice_lambda_f64 / ttlda_mstep_slice_beta_f64 — the per-rank halves of the sharded M-step, here with
+    the N "ranks" emulated on one GPU: N source statistics tables summed in order inside phase A (what the peer-mapped
+    NVLink loads do), every slice's exp(E[log beta]) rows stored into N destination tables in phase B (the NVLink
+    stores) — against ttlda_mstep_f64 on the pre-summed table."""
+    g = torch.Generator(device="cpu").manual_seed(11 * K + V)
+    ld = nv.ld_for(K)
+    Vs = -(-V // N)
+    Vp = Vs * N
+    parts = [torch.zeros((Vp, ld), dtype=torch.float64) for _ in range(N)]
+    for t in parts:
+        t[:V, :K] = torch.rand((V, K), generator=g, dtype=torch.float64) * 3
+    eB0 = torch.zeros((Vp, ld), dtype=torch.float64)
+    eB0[:V, :K] = torch.rand((V, K), generator=g, dtype=torch.float64) + 0.01
+    parts = [t.to(dev) for t in parts]
+    eta = 0.7
+    # reference: full M-step on the sum
+    S = torch.stack(parts).sum(0)[:V].contiguous()
+    eB_ref, lam_ref = eB0[:V].clone().to(dev), torch.zeros((V, ld), dtype=torch.float64, device=dev)
+    colsum_ref, part_ref = torch.zeros(ld, dtype=torch.float64, device=dev), torch.zeros(nv.NPART, dtype=torch.float64, device=dev)
+    ws = torch.empty(nv.mstep_workspace_bytes(V, ld), dtype=torch.uint8, device=dev)
+    nv.mstep(S, K, eta, eB_ref, lam_ref, None, colsum_ref, part_ref, ws)
+    # sharded: every "rank" has its own copy of the old eB, its lambda table, and receives every slice's new eB rows
+    eBs = [eB0.clone().to(dev) for _ in range(N)]
+    lams = [torch.zeros((Vp, ld), dtype=torch.float64, device=dev) for _ in range(N)]
+    colparts = torch.zeros((N, ld), dtype=torch.float64, device=dev)
+    for r in range(N):
+        w0 = r * Vs
+        n = max(0, min(Vs, V - w0))
+        nv.mstep_slice_lambda([t.data_ptr() for t in parts], w0, w0, n, K, eta, eBs[r], lams[r], colparts[r], ws)
+    beta_total = 0.0
+    colsum = torch.zeros(ld, dtype=torch.float64, device=dev)
+    for r in range(N):
+        w0 = r * Vs
+        n = max(0, min(Vs, V - w0))
+        pr = torch.zeros(nv.NPART, dtype=torch.float64, device=dev)
+        nv.mstep_slice_beta(colparts, w0, n, K, eta, lams[r], [t.data_ptr() for t in eBs], r == 0, colsum, pr, ws)
+        beta_total += float(pr[0].item())
+    lam = torch.zeros((V, ld), dtype=torch.float64, device=dev)
+    for r in range(N):
+        w0 = r * Vs
+        n = max(0, min(Vs, V - w0))
+        lam[w0:w0 + n] = lams[r][w0:w0 + n]
+    assert relerr(lam.cpu().numpy(), lam_ref.cpu().numpy()) < 1e-14
+    assert relerr(colsum.cpu().numpy()[:K], colsum_ref.cpu().numpy()[:K]) < 1e-14
+    for t in eBs:  # every destination table received every slice
+        assert relerr(t[:V].cpu().numpy(), eB_ref.cpu().numpy()) < 1e-12
+        assert torch.equal(t, eBs[0]) and float(t[V:].abs().sum()) == 0.0
+    assert abs(beta_total - float(part_ref[0].item())) <= 1e-12 * abs(float(part_ref[0].item()))
+
+
 def test_cfg5_class_shapes_plan_the_windowed_pass():
     """The planner picks the windowed pass where rows are long (cfg4: K = 500; cfg5: K = 1000, where whole-row blocks
     could not be afforded at all) and keeps whole rows at cfg3."""

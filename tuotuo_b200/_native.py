@@ -64,6 +64,10 @@ SIGNATURES = {
                                               _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
                                               _ptr]),
+    "ttlda_mstep_slice_lambda_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr,
+                                                    _i64, _ptr]),
+    "ttlda_mstep_slice_beta_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _i64, ctypes.c_int,
+                                                  _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
                                              _ptr]),
     "ttlda_hyper_stats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
@@ -92,7 +96,7 @@ KERNELS_PER_CALL = {
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_hot_f64": 2, "ttlda_build_estream": 1, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_csc_windowed_f64": 0, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
-    "ttlda_beta_refresh_f64": 4, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_hyper_colstats_f64": 2, "ttlda_psi_f64": 1,
+    "ttlda_beta_refresh_f64": 4, "ttlda_mstep_slice_lambda_f64": 2, "ttlda_mstep_slice_beta_f64": 3, "ttlda_elbo_tokens_f64": 2, "ttlda_hyper_stats_f64": 2, "ttlda_hyper_colstats_f64": 2, "ttlda_psi_f64": 1,
     "ttlda_transpose_pad_f64": 1, "ttlda_transpose_unpad_f64": 1, "ttlda_probe_gather_f64": 1,
 }
 
@@ -382,6 +386,32 @@ def mstep_online(sstats, K, eta, scale, rho, eB, lam, elogbeta, colsum, partial,
     _call("ttlda_mstep_online_f64", _p(sstats, f64), V, int(K), ld, float(eta), float(scale), float(rho), _p(eB, f64),
           _p(lam, f64), _p(elogbeta, f64), _p(colsum, f64), _p(partial, f64), _p(ws), ws.numel() * ws.element_size(),
           _stream())
+
+
+def _ptr_array(ptrs):
+    """Host array of device pointers (ints) for the peer-table arguments; returns (ctypes array, device index or None)."""
+    arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+    return arr
+
+
+def mstep_slice_lambda(src_ptrs, src_row0, w0, n, K, eta, eB, lam, colsum_part, ws):
+    """Phase A of the sharded M-step on rows [w0, w0+n): src_ptrs = device addresses (ints) of the statistics tables to
+    sum in order — peer-mapped tables of every rank, or one locally reduced buffer."""
+    ld = eB.shape[1]
+    arr = _ptr_array(src_ptrs)
+    _call("ttlda_mstep_slice_lambda_f64", ctypes.cast(arr, ctypes.c_void_p), len(src_ptrs), int(src_row0), int(w0),
+          int(n), int(K), ld, float(eta), _p(eB, f64), _p(lam, f64), _p(colsum_part, f64), _p(ws),
+          ws.numel() * ws.element_size(), _stream())
+
+
+def mstep_slice_beta(colsum_parts, w0, n, K, eta, lam, dst_ptrs, add_colsum_term, colsum, partial, ws):
+    """Phase B: colsum_parts [nparts][ld] (rank order) -> colsum; exp(E[log beta]) rows [w0, w0+n) stored into every table
+    of dst_ptrs (device addresses: this rank's table, or all ranks' through peer memory)."""
+    nparts, ld = colsum_parts.shape
+    arr = _ptr_array(dst_ptrs)
+    _call("ttlda_mstep_slice_beta_f64", _p(colsum_parts, f64), nparts, int(w0), int(n), int(K), ld, float(eta),
+          _p(lam, f64), ctypes.cast(arr, ctypes.c_void_p), len(dst_ptrs), int(bool(add_colsum_term)), _p(colsum, f64),
+          _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 
 def beta_refresh(lam, K, eta, eB, elogbeta, colsum, partial, ws):

@@ -126,6 +126,116 @@ __global__ void __launch_bounds__(256) beta_refresh_kernel(const double* __restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Sharded M-step (documents AND the vocabulary are split over the ranks): rank r owns the rows [w0, w0 + n) of lambda.
+// The two kernels below are the per-slice halves of the three above, with the cross-rank exchanges FUSED into them when
+// the statistics / exp(E[log beta]) tables live in peer-mapped memory (NVLink): phase A sums the `nsrc` ranks' statistics
+// rows with plain loads through the peer pointers, in rank order (the reduce-scatter, bit-identical on every rank);
+// phase B stores every new exp(E[log beta]) row into all `ndst` ranks' tables (the all-gather).  With nsrc = ndst = 1
+// they run on buffers a library collective has reduced / will gather.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;  // ranks of one NVLink domain (one node)
+struct PeerTables {
+    const double* src[kMaxPeers];
+    double* dst[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(256) mstep_slice_lambda_kernel(const PeerTables T, int nsrc, int64_t src_row0,
+                                                                 int64_t w0, int64_t n, int K, int64_t ld, double eta,
+                                                                 const double* __restrict__ eB,
+                                                                 double* __restrict__ lambda,
+                                                                 double* __restrict__ colpart)
+{
+    extern __shared__ double sm_cols[];  // [TY][ld]
+    const int TX = blockDim.x, TY = blockDim.y, tx = threadIdx.x, ty = threadIdx.y;
+    const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t b0 = (int64_t)blockIdx.x * per, b1 = (b0 + per < n) ? b0 + per : n;
+    double cs[kMaxJ];
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) cs[j] = 0.;
+    for (int64_t wl = b0 + ty; wl < b1; wl += TY) {
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) {
+            const int k = tx + TX * j;
+            if (k < (int)ld) {
+                const int64_t is = (src_row0 + wl) * ld + k, idx = (w0 + wl) * ld + k;
+                double lam = 0.;
+                if (k < K) {
+                    // statistics of all ranks (lda_model.py:262 over every shard): the loads — NVLink round trips when the
+                    // tables are peer-mapped — are all issued before the first add; the sum runs in rank order
+                    double v[kMaxPeers];
+#pragma unroll
+                    for (int i = 0; i < kMaxPeers; ++i) v[i] = (i < nsrc) ? T.src[i][is] : 0.;
+                    double sum = v[0];
+#pragma unroll
+                    for (int i = 1; i < kMaxPeers; ++i) sum += v[i];  // + 0.0 for i >= nsrc: exact
+                    lam = eta + sum * eB[idx];  // lda_model.py:264 then :280
+                }
+                lambda[idx] = lam;
+                cs[j] += lam;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxJ; ++j) {
+        const int k = tx + TX * j;
+        if (k < (int)ld) sm_cols[ty * ld + k] = cs[j];
+    }
+    __syncthreads();
+    if (ty == 0) {
+#pragma unroll
+        for (int j = 0; j < kMaxJ; ++j) {
+            const int k = tx + TX * j;
+            if (k < (int)ld) {
+                double s = 0.;
+                for (int y = 0; y < TY; ++y) s += sm_cols[y * ld + k];
+                colpart[(int64_t)blockIdx.x * ld + k] = s;
+            }
+        }
+    }
+}
+
+// column sums of the slice in fixed CTA order
+__global__ void colsum_slice_kernel(const double* __restrict__ colpart, int nblocks, int64_t ld, double* __restrict__ out)
+{
+    for (int k = threadIdx.x; k < (int)ld; k += blockDim.x) {
+        double s = 0.;
+        for (int b = 0; b < nblocks; ++b) s += colpart[(int64_t)b * ld + k];
+        out[k] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) beta_slice_kernel(const double* __restrict__ lambda, int64_t w0, int64_t n, int K,
+                                                         int64_t ld, double eta, const double* __restrict__ psi_colsum,
+                                                         const double* __restrict__ extra, int add_extra,
+                                                         const PeerTables T, int ndst, double* __restrict__ records)
+{
+    __shared__ double sm[32];
+    const int64_t total = n * ld, base = w0 * ld;
+    const double lg_eta = lgamma(eta);
+    double t[1] = {0.};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % ld);
+        double x = 0.;
+        if (k < K) {
+            const double lam = lambda[base + i];
+            double ps, lg;
+            psi_lgamma_as103(lam, ps, lg);
+            const double e = ps - psi_colsum[k];      // cutils.pyx:65-66
+            x = exp(e);
+            t[0] += (eta - lam) * e + (lg - lg_eta);  // lda_model.py:40-41
+        }
+        for (int d = 0; d < ndst; ++d) T.dst[d][base + i] = x;  // this rank's table and, over NVLink, every peer's
+    }
+    block_sum<1>(t, sm);
+    if (threadIdx.x == 0) {
+        double* rec = records + (size_t)blockIdx.x * NPART;
+        rec[0] = t[0] + ((blockIdx.x == 0 && add_extra) ? extra[0] : 0.);
+#pragma unroll
+        for (int j = 1; j < NPART; ++j) rec[j] = 0.;
+    }
+}
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 static int64_t mstep_ws_bytes(int64_t ld)
@@ -201,6 +311,71 @@ int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t l
     TTLDA_REQUIRE(rho > 0. && rho <= 1. && scale > 0., "need 0 < rho <= 1 and scale > 0");
     return run_mstep<2>(sstats, V, K, ld, eta, scale, rho, exp_elogbeta, lambda, elogbeta_out, colsum_out, partial_out,
                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, int64_t src_row0, int64_t w0, int64_t n,
+                                 int64_t K, int64_t ld, double eta, const double* exp_elogbeta, double* lambda,
+                                 double* colsum_part_out, void* workspace, int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(src_tables && exp_elogbeta && lambda && colsum_part_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(nsrc >= 1 && nsrc <= kMaxPeers, "1 <= nsrc <= 8");
+    TTLDA_REQUIRE(w0 >= 0 && n >= 0 && src_row0 >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
+    if (workspace_bytes < mstep_ws_bytes(ld)) {
+        set_error("mstep_slice_lambda: workspace %lld < %lld", (long long)workspace_bytes, (long long)mstep_ws_bytes(ld));
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerTables T{};
+    for (int i = 0; i < nsrc; ++i) {
+        TTLDA_REQUIRE(src_tables[i], "NULL source table");
+        T.src[i] = src_tables[i];
+    }
+    double* colpart = (double*)((char*)workspace + align256((size_t)reduce_ws_bytes()));
+    int TX = 32;
+    while (TX < 256 && TX < ld) TX *= 2;
+    if (ld > 64 && TX < 128) TX = 128;
+    const int TY = 256 / TX;
+    const int nblocks = (int)(n < kColBlocks ? (n > 0 ? n : 1) : kColBlocks);
+    mstep_slice_lambda_kernel<<<nblocks, dim3(TX, TY), (size_t)TY * ld * sizeof(double), s>>>(
+        T, (int)nsrc, src_row0, w0, n, (int)K, ld, eta, exp_elogbeta, lambda, colpart);
+    TTLDA_LAUNCH_CHECK("mstep_slice_lambda");
+    colsum_slice_kernel<<<1, 256, 0, s>>>(colpart, nblocks, ld, colsum_part_out);
+    TTLDA_LAUNCH_CHECK("colsum_slice");
+    return TTLDA_OK;
+}
+
+int ttlda_mstep_slice_beta_f64(const double* colsum_parts, int64_t nparts, int64_t w0, int64_t n, int64_t K, int64_t ld,
+                               double eta, const double* lambda, double* const* dst_tables, int64_t ndst,
+                               int add_colsum_term, double* colsum_out, double* partial_out, void* workspace,
+                               int64_t workspace_bytes, void* stream)
+{
+    TTLDA_REQUIRE(colsum_parts && lambda && dst_tables && colsum_out && partial_out && workspace, "NULL pointer");
+    TTLDA_REQUIRE(nparts >= 1 && nparts <= kColBlocks && ndst >= 1 && ndst <= kMaxPeers, "bad rank counts");
+    TTLDA_REQUIRE(w0 >= 0 && n >= 0 && K >= 1 && K <= TTLDA_MAX_K && ld >= K && ld % 4 == 0, "bad shape");
+    if (workspace_bytes < mstep_ws_bytes(ld)) {
+        set_error("mstep_slice_beta: workspace %lld < %lld", (long long)workspace_bytes, (long long)mstep_ws_bytes(ld));
+        return TTLDA_EWORKSPACE;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    PeerTables T{};
+    for (int i = 0; i < ndst; ++i) {
+        TTLDA_REQUIRE(dst_tables[i], "NULL destination table");
+        T.dst[i] = dst_tables[i];
+    }
+    char* ws = (char*)workspace;
+    double* records = (double*)ws;
+    double* psi_colsum = (double*)(ws + align256((size_t)reduce_ws_bytes()) + align256((size_t)kColBlocks * ld * sizeof(double)));
+    double* extra = (double*)((char*)psi_colsum + align256((size_t)ld * sizeof(double)));
+    // global column sums = the ranks' partials in rank order (identical bits everywhere), psi~ of them, colsum-only term
+    colsum_finish_kernel<<<1, 256, 0, s>>>(colsum_parts, (int)nparts, (int)K, ld, eta, colsum_out, psi_colsum, extra);
+    TTLDA_LAUNCH_CHECK("colsum_finish");
+    const int64_t total = n * ld;
+    int grid = (int)((total + 255) / 256 < (int64_t)kSMs * 8 ? (total + 255) / 256 : (int64_t)kSMs * 8);
+    if (grid < 1) grid = 1;
+    beta_slice_kernel<<<grid, 256, 0, s>>>(lambda, w0, n, (int)K, ld, eta, psi_colsum, extra, add_colsum_term, T,
+                                           (int)ndst, records);
+    TTLDA_LAUNCH_CHECK("beta_slice");
+    return launch_reduce_records(records, grid, partial_out, s);
 }
 
 int ttlda_beta_refresh_f64(const double* lambda, int64_t V, int64_t K, int64_t ld, double eta, double* exp_elogbeta,

@@ -130,6 +130,78 @@ class LDASmoothed:
         st = self._st
         st.alpha_vec = torch.as_tensor(self._alpha_vec_host().copy()).to(st.dev)
 
+    def _alloc_topic_tables(self, st, sharded_ok: bool):
+        """lambda / exp(E[log beta]) / statistics tables [V][ld].  On one GPU: plain tensors.  Document-sharded over N
+        ranks (NCCL): the M-step is SHARDED over the vocabulary as well — rank r owns rows [r*Vs, (r+1)*Vs) of lambda —
+        so the tables get V_pad = N*Vs rows, and (mode "peer", the default when the ranks share an NVLink domain) the
+        statistics and exp(E[log beta]) tables are allocated as symmetric memory: every rank maps every rank's table,
+        the reduce-scatter of the statistics becomes plain NVLink loads inside ttlda_mstep_slice_lambda_f64 and the
+        all-gather of exp(E[log beta]) plain NVLink stores inside ttlda_mstep_slice_beta_f64.  Mode "nccl" does the two
+        exchanges with library collectives around the same kernels; "replicated" is round 1's all-reduce + a full
+        M-step on every rank.  TTLDA_MSTEP selects; a failed symmetric-memory rendezvous degrades to "nccl"."""
+        dev, V, ld = st.dev, st.V, st.ld
+        f64 = torch.float64
+        dist = self._dist()
+        mode = "local"
+        if dist is not None:
+            mode = os.environ.get("TTLDA_MSTEP", "peer")
+            if mode not in ("peer", "nccl", "replicated"):
+                raise ValueError("TTLDA_MSTEP must be peer, nccl or replicated")
+            if not sharded_ok or dist.get_backend() != "nccl" or dev.type != "cuda" or dist.get_world_size() > 8:
+                mode = "replicated"
+        st.mstep_mode, st.lam_synced, st.beta_sharded = mode, True, False
+        if mode in ("local", "replicated"):
+            st.lam = torch.zeros((V, ld), dtype=f64, device=dev)
+            st.eB = torch.zeros((V, ld), dtype=f64, device=dev)
+            st.sstats = torch.zeros((V, ld), dtype=f64, device=dev)
+            return
+        N, r = dist.get_world_size(), dist.get_rank()
+        Vs = -(-V // N)
+        st.Vs, st.w0 = Vs, r * Vs
+        st.wn = max(0, min(Vs, V - st.w0))
+        Vp = N * Vs
+        st.symm = None
+        if mode == "peer":
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                group = dist.group.WORLD
+                if hasattr(symm, "enable_symm_mem_for_group") and not symm.is_symm_mem_enabled_for_group(group.group_name):
+                    symm.enable_symm_mem_for_group(group.group_name)
+                st.sstats_pad = symm.empty((Vp, ld), dtype=f64, device=dev)
+                st.eB_pad = symm.empty((Vp, ld), dtype=f64, device=dev)
+                hs, hb = symm.rendezvous(st.sstats_pad, group), symm.rendezvous(st.eB_pad, group)
+                st.S_ptrs, st.eB_ptrs = [int(p) for p in hs.buffer_ptrs], [int(p) for p in hb.buffer_ptrs]
+                if len(st.S_ptrs) != N or len(st.eB_ptrs) != N:
+                    raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peers")
+                st.symm = hs
+                st.sstats_pad.zero_()
+                st.eB_pad.zero_()
+                ok = 1
+            except Exception as e:  # no peer mapping on this system (no NVLink / fabric handles refused)
+                st.peer_error = f"{type(e).__name__}: {e}"
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank takes the same path
+            if int(flag.item()) == 0:
+                mode = st.mstep_mode = "nccl"
+                st.symm = None
+        if mode == "nccl":
+            st.sstats_pad = torch.zeros((Vp, ld), dtype=f64, device=dev)
+            st.eB_pad = torch.zeros((Vp, ld), dtype=f64, device=dev)
+            st.S_slice = torch.zeros((Vs, ld), dtype=f64, device=dev)
+        st.lam_pad = torch.zeros((Vp, ld), dtype=f64, device=dev)
+        st.lam, st.eB, st.sstats = st.lam_pad[:V], st.eB_pad[:V], st.sstats_pad[:V]
+        st.colpart_mine = torch.zeros(ld, dtype=f64, device=dev)
+        st.colparts = torch.zeros((N, ld), dtype=f64, device=dev)
+
+    def _sync_lambda(self):
+        """After a sharded M-step every rank holds only its own rows of lambda: gather them before any full-table use."""
+        st = self._st
+        if st is not None and not getattr(st, "lam_synced", True):
+            self._dist().all_gather_into_tensor(st.lam_pad, st.lam_pad[st.w0:st.w0 + st.Vs])
+            st.lam_synced = True
+
     def _alloc_state(self, corpus: DeviceCorpus, topics_from=None):
         """Device tensors for `corpus`.  topics_from: a previous state whose topic-side tables (lambda, exp(E[log beta]),
         column sums, beta-prior record) are carried over (online learning: the documents change, the topics persist)."""
@@ -145,9 +217,7 @@ class LDASmoothed:
         st.gamma = [torch.zeros((D, ld), dtype=f64, device=dev), torch.zeros((D, ld), dtype=f64, device=dev)]
         st.eT = [torch.zeros((D, ld), dtype=f64, device=dev), torch.zeros((D, ld), dtype=f64, device=dev)]
         st.cur = 0
-        st.lam = torch.zeros((V, ld), dtype=f64, device=dev)
-        st.eB = torch.zeros((V, ld), dtype=f64, device=dev)
-        st.sstats = torch.zeros((V, ld), dtype=f64, device=dev)
+        self._alloc_topic_tables(st, sharded_ok=topics_from is None)
         st.colsum = torch.zeros(ld, dtype=f64, device=dev)
         st.part = torch.zeros((5, nv.NPART), dtype=f64, device=dev)
         st.iters = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -187,6 +257,7 @@ class LDASmoothed:
             raise AttributeError("'LDASmoothed' object has no attribute '_lambda_'")
         if "lam" not in self._np_cache:
             st = self._st
+            self._sync_lambda()  # collective when the M-step is sharded: call it on every rank
             out = torch.empty((st.K, st.V), dtype=torch.float64, device=st.dev)
             nv.transpose_unpad(st.lam, st.K, out)
             self._np_cache["lam"] = out.cpu().numpy()
@@ -200,6 +271,7 @@ class LDASmoothed:
         v = torch.as_tensor(np.ascontiguousarray(value, dtype=np.float64)).to(st.dev)
         assert v.shape == (st.K, st.V)
         nv.transpose_pad(v, st.lam)
+        st.lam_synced = True
         self._np_cache.pop("lam", None)
 
     @property
@@ -250,7 +322,9 @@ class LDASmoothed:
 
     def _refresh_beta(self):
         st = self._st
+        self._sync_lambda()
         nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB, None, st.colsum, st.part[2], st.ws_m)
+        st.beta_sharded = False  # every rank now holds the complete beta-prior term
 
     def _tokens(self):
         st, c = self._st, self._st.corpus
@@ -325,9 +399,14 @@ class LDASmoothed:
             self._sstats_pass(eT, st.ratio if use_ratio else None)
         dist = self._dist()
         work = None
-        if dist is not None:  # NCCL sum of the K x V statistics over NVLink, asynchronous:
-            work = dist.all_reduce(st.sstats, async_op=True)  # the theta refresh below overlaps it
-            if nv.timing is not None:  # bench.py: from issuing the collective to the M-step's start
+        if dist is not None:
+            # sum of the K x V statistics over the document shards; the theta refresh below overlaps it
+            if st.mstep_mode == "replicated":
+                work = dist.all_reduce(st.sstats, async_op=True)
+            elif st.mstep_mode == "nccl":  # every rank receives the sum of ITS rows only
+                work = dist.reduce_scatter_tensor(st.S_slice, st.sstats_pad, async_op=True)
+            # "peer": nothing to launch — the M-step's first kernel reads the peers' tables itself
+            if nv.timing is not None:  # bench.py: from here to the M-step's first kernel
                 st.ev_ar = torch.cuda.Event(enable_timing=True)
                 st.ev_ar.record()
         if not (self._inner_fixed_point or self._fused_refresh):
@@ -345,12 +424,34 @@ class LDASmoothed:
             st.part[1, 0].copy_(st.part[4, 0])
         if work is not None:
             work.wait()
-            if nv.timing is not None and getattr(st, "ev_ar", None) is not None:
-                e1 = torch.cuda.Event(enable_timing=True)
-                e1.record()
-                nv.timing.setdefault("nccl_allreduce_to_mstep", []).append((st.ev_ar, e1))
-                st.ev_ar = None
-        if online is None:
+        mode = getattr(st, "mstep_mode", "local")
+        if mode == "peer":
+            st.symm.barrier(channel=0)  # every rank's statistics pass has finished: its table may be read over NVLink
+        if nv.timing is not None and getattr(st, "ev_ar", None) is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            nv.timing.setdefault("exchange_to_mstep", []).append((st.ev_ar, e1))
+            st.ev_ar = None
+        if mode in ("peer", "nccl"):
+            if online is not None:
+                raise nv.TTLDAError("the online M-step runs replicated")
+            dist = self._dist()
+            eta = float(self._eta_)
+            src = st.S_ptrs if mode == "peer" else [st.S_slice.data_ptr()]
+            nv.mstep_slice_lambda(src, st.w0 if mode == "peer" else 0, st.w0, st.wn, st.K, eta, st.eB, st.lam,
+                                  st.colpart_mine, st.ws_m)
+            # K column sums per rank: a 8K-byte exchange that is also the point after which no rank reads the others'
+            # statistics any more (the next statistics pass may overwrite them)
+            dist.all_gather_into_tensor(st.colparts, st.colpart_mine)
+            dst = st.eB_ptrs if mode == "peer" else [st.eB.data_ptr()]
+            nv.mstep_slice_beta(st.colparts, st.w0, st.wn, st.K, eta, st.lam, dst, dist.get_rank() == 0, st.colsum,
+                                st.part[2], st.ws_m)
+            if mode == "peer":
+                st.symm.barrier(channel=1)  # all ranks' rows of exp(E[log beta]) have landed in this rank's table
+            else:
+                dist.all_gather_into_tensor(st.eB_pad, st.eB_pad[st.w0:st.w0 + st.Vs])
+            st.lam_synced, st.beta_sharded = False, True
+        elif online is None:
             nv.mstep(st.sstats, st.K, float(self._eta_), st.eB, st.lam, None, st.colsum, st.part[2], st.ws_m)
         else:  # (scale, rho): stochastic natural-gradient step on lambda (partial_fit)
             nv.mstep_online(st.sstats, st.K, float(self._eta_), online[0], online[1], st.eB, st.lam, None, st.colsum,
@@ -614,8 +715,13 @@ class LDASmoothed:
         saved = self._inner_fixed_point
         self._inner_fixed_point = True  # documents are solved to their fixed point, not with the frozen-theta loop
         try:
+            if not first:
+                self._sync_lambda()  # a sharded batch M-step leaves every rank with its own rows of lambda only
+                resharded = getattr(self._st, "beta_sharded", False)
             st = self._alloc_state(corpus, topics_from=None if first else self._st)
             K, V = st.K, st.V
+            if not first and resharded:
+                self._refresh_beta()  # complete beta-prior term on every rank (the online M-step runs replicated)
             if first:
                 np.random.seed(SEED)  # lda_model.py:356-357
                 lam0 = np.random.gamma(shape=100, scale=0.01, size=(K, V)).astype(DTYPE, copy=False)
@@ -659,11 +765,15 @@ class LDASmoothed:
         keeps launching (statistics pass, theta refresh) before it asks for the result."""
         st = self._st
         flags = st.flags.to(torch.float64)
+        # [tok, theta, count, passes, capped, flags, beta (this rank's share, sharded M-step) | beta (replicated)]
+        beta = st.part[2, 0:1]
+        zero = torch.zeros_like(beta)
+        sharded = getattr(st, "beta_sharded", False)
         buf = torch.cat([torch.stack([st.part[tok_row, 0], st.part[1, 0], st.part[tok_row, 2],
                                       st.iters[0].to(torch.float64), st.iters[1].to(torch.float64)]),
-                         flags, st.part[2, 0:1]])  # [tok, theta, count, passes, capped, flags | beta (replicated)]
+                         flags, beta if sharded else zero, zero if sharded else beta])
         dist = self._dist()
-        work = dist.all_reduce(buf[:6], async_op=True) if dist is not None else None
+        work = dist.all_reduce(buf[:7], async_op=True) if dist is not None else None
         if st.dev.type != "cuda":  # only reachable with the test-only CPU stand-ins (tests/cpu_kernels.py, gloo)
             if work is not None:
                 work.wait()
@@ -671,7 +781,7 @@ class LDASmoothed:
             return None
         if getattr(self, "_side_stream", None) is None:
             self._side_stream = torch.cuda.Stream(device=st.dev)
-            self._host_terms = torch.empty(7, dtype=torch.float64).pin_memory()
+            self._host_terms = torch.empty(8, dtype=torch.float64).pin_memory()
         main = torch.cuda.current_stream(st.dev)
         side = self._side_stream
         side.wait_stream(main)
@@ -695,7 +805,7 @@ class LDASmoothed:
             st.flags.zero_()
             raise ValueError(nv.bad_corpus_message(int(h[5]) if self._dist() is None else 7)
                              + " — the iteration was not committed")
-        st.terms = dict(tok=float(h[0]), theta=float(h[1]), beta=float(h[6]), count=float(h[2]))
+        st.terms = dict(tok=float(h[0]), theta=float(h[1]), beta=float(h[6]) + float(h[7]), count=float(h[2]))
         return int(h[3]), int(h[4])
 
     def _collect(self, tok_row: int):
@@ -815,6 +925,7 @@ class LDASmoothed:
     def _lambda_psi_stat(self) -> float:
         """sum_kv psi(lambda_kv) - V * sum_k psi(sum_v lambda_kv)   (lda_model.py:522-528)."""
         st = self._st
+        self._sync_lambda()
         nv.hyper_stats(st.lam, st.K, st.part[4], st.ws)
         pc = torch.empty(st.K, dtype=torch.float64, device=st.dev)
         nv.psi_exact(st.colsum[:st.K].contiguous(), pc)
@@ -901,6 +1012,7 @@ class LDASmoothed:
     # ------------------------------------------------------------------------------------------------------------------
     def _elog_np(self):
         st = self._st
+        self._sync_lambda()
         et = torch.empty_like(st.gamma[st.cur])
         nv.dirichlet_expectation(st.gamma[st.cur], st.K, out_elog=et)
         eb = torch.empty_like(st.lam)
@@ -937,7 +1049,9 @@ class LDASmoothed:
         self._load_elogs(expec_log_theta, expec_log_beta)
         self._refresh_theta_term_only()
         st = self._st
+        self._sync_lambda()
         nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB.clone(), None, st.colsum, st.part[2], st.ws_m)
+        st.beta_sharded = False
         self._tokens()
         self._collect(tok_row=3)
         self._perplexity_from_terms(sampling)
@@ -992,6 +1106,7 @@ class LDASmoothed:
         st = self._st
         lam = float(self._eta_) + torch.as_tensor(np.ascontiguousarray(lambda_update, dtype=np.float64)).to(st.dev)
         nv.transpose_pad(lam, st.lam)
+        st.lam_synced, st.beta_sharded = True, False
         self._invalidate("lam")
         eb = torch.empty_like(st.lam)
         nv.beta_refresh(st.lam, st.K, float(self._eta_), st.eB, eb, st.colsum, st.part[2], st.ws_m)
