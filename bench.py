@@ -371,6 +371,14 @@ def measure(ctx, name, doc, K, V, steps, warmup, *, sampling=False, e2e=False, f
 
     # ---- collectives, timed alone on this rank's buffers (N > 1) -------------------------------------------------------
     if world > 1:
+        # every rank's own kernel time per step: the step runs at the pace of the slowest GPU (the ranks meet at the
+        # statistics exchange), so the spread of this list is what weak scaling loses before any communication cost
+        mine = torch.tensor([sum(v for k, v in per_kernel.items() if k.startswith("ttlda_")), ms_local / steps],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        res["per_rank"] = {"kernel_ms": [round(float(t[0]), 3) for t in allr],
+                           "step_ms": [round(float(t[1]), 3) for t in allr]}
         work = st.sstats.clone()
         for _ in range(2):
             dist.all_reduce(work)
@@ -387,6 +395,7 @@ def measure(ctx, name, doc, K, V, steps, warmup, *, sampling=False, e2e=False, f
                             "bus_GBps": round(2 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9, 1),
                             "exchange_to_mstep_ms": per_kernel.get("exchange_to_mstep"),
                             "mstep_mode": st.mstep_mode, "peer_error": getattr(st, "peer_error", None),
+                            "nvswitch_multicast": bool(getattr(st, "S_mc", 0)),
                             "note": "ms_alone = an NCCL all-reduce of a table of this size by itself, for reference; the "
                                     "iteration itself exchanges the statistics in mode `mstep_mode`: peer = NVLink loads / "
                                     "stores fused into the sharded M-step kernels (their times are in kernel_ms), nccl = "
@@ -680,6 +689,7 @@ def run_ours(args):
                 "fit_call": main.get("fit_call"), "perplexity_trace": main["perplexity_trace"]}
         if "allreduce" in main:
             line["allreduce"] = main["allreduce"]
+            line["per_rank"] = main.get("per_rank")
         if parity is not None:
             line["multigpu_parity"] = parity
         if extra:

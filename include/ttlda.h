@@ -298,14 +298,20 @@ int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t l
  *            dst_tables (host array of device pointers: this rank's table, or all ranks' through peer memory — the
  *            all-gather fused into the kernel as NVLink stores); partial_out[0] = the slice's share of the beta-prior
  *            term (+ the colsum-only part iff add_colsum_term, which exactly one rank passes).
+ * src_multicast / dst_multicast (may be NULL): the NVSwitch MULTICAST address of the same tables (NVLink SHARP).  When
+ * given, phase A reads the cross-rank sum with one multimem.ld_reduce.add.f64 per element — the reduction happens in the
+ * switch and this rank's link carries its slice once instead of once per peer — and phase B replicates every row into
+ * all ranks' tables with one multimem.st; src_tables / dst_tables are then only checked.  The in-switch summation order
+ * is the hardware's (each lambda row is still computed by exactly one rank, so the ranks cannot disagree).
  * Workspace for both: ttlda_mstep_workspace_bytes.  lambda / exp_elogbeta are this rank's full [V][ld] tables.
  */
-int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, int64_t src_row0, int64_t w0, int64_t n,
+int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, const double* src_multicast,
+                                 int64_t src_row0, int64_t w0, int64_t n,
                                  int64_t K, int64_t ld, double eta, const double* exp_elogbeta, double* lambda,
                                  double* colsum_part_out, void* workspace, int64_t workspace_bytes, void* stream);
 int ttlda_mstep_slice_beta_f64(const double* colsum_parts, int64_t nparts, int64_t w0, int64_t n, int64_t K, int64_t ld,
                                double eta, const double* lambda, double* const* dst_tables, int64_t ndst,
-                               int add_colsum_term, double* colsum_out, double* partial_out,
+                               double* dst_multicast, int add_colsum_term, double* colsum_out, double* partial_out,
                                void* workspace, int64_t workspace_bytes, void* stream);
 
 /* beta refresh from an existing lambda (initial state, or after a hyper-parameter update):

@@ -608,6 +608,29 @@ def test_sharded_mstep_slices_equal_full_mstep(nv, dev, K, V, N):
     assert abs(beta_total - float(part_ref[0].item())) <= 1e-12 * abs(float(part_ref[0].item()))
 
 
+@pytest.mark.parametrize("D,V,blocks", [(700, 900, 1), (2500, 70_000, 3), (40, 12, 2), (65, 58_200, 1)])
+def test_counting_sort_mirror_equals_sorted_mirror(monkeypatch, dev, D, V, blocks):
+    """The opt-in mirror by counting sort (32-document tiles, order-free bitmask ranks; TTLDA_CSC_TILES=1) builds the
+    same colptr / docidx / ccounts / csr2csc, bit for bit, as the default CUB-sort path — including a vocabulary that
+    needs two word ranges (V > 58 112) and a ragged last tile."""
+    from tuotuo_b200.corpus import DeviceCorpus
+    from tuotuo_b200.synth import numpy_corpus
+
+    rp, ci, ct = numpy_corpus(300 + D, D, V, 8, 30, ragged=True)
+    out = []
+    for tiles in ("0", "1"):
+        monkeypatch.setenv("TTLDA_CSC_TILES", tiles)
+        c = DeviceCorpus.from_host_csr(rp, ci, ct, V, dev)
+        c.build_csc(blocks)
+        out.append([t.clone() for t in (c.colptr, c.docidx[:c.nnz], c.ccounts[:c.nnz], c.csr2csc[:c.nnz])])
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+    docs = np.repeat(np.arange(D), np.diff(rp))
+    bd = -(-D // blocks)
+    order = np.argsort((docs // bd) * V + ci, kind="stable")
+    assert np.array_equal(out[1][1].cpu().numpy(), docs[order])
+
+
 def test_cfg5_class_shapes_plan_the_windowed_pass():
     """The planner picks the windowed pass where rows are long (cfg4: K = 500; cfg5: K = 1000, where whole-row blocks
     could not be afforded at all) and keeps whole rows at cfg3."""

@@ -159,3 +159,37 @@ def test_from_csr_rejects_malformed_corpora():
                 (rp, np.array([1, 3, 0, 2, 2 ** 32 + 1]), ct)]:
         with pytest.raises(ValueError):
             Document.from_csr(*bad, 5)
+
+
+def test_corpus_tokenizer_equals_per_document_pipeline():
+    """text.tokenize_corpus (one vectorised pass over the whole corpus) yields exactly what the reference's
+    per-document `text_pipeline(doc).split(' ')` + first-appearance ids do (tuotuo/utils.py:71-98,177-206): accents,
+    special characters, punctuation, whitespace runs, stop words, empty documents ('' gets a vocabulary id)."""
+    import random
+
+    import numpy as np
+
+    from tuotuo_b200.document import Document
+    from tuotuo_b200.text import text_pipeline, tokenize_corpus
+
+    random.seed(3)
+    words = ["the", "Olympic", "FIFA", "not", "café", "naïve", "hello", "world", "don't", "isn't", "a", "I", "x1",
+             "42", "re-use", "e.g.", "…", "日本", "tab\there", "new\nline", "", "  ", "^caret", "a_b"]
+
+    def make():
+        return " ".join(random.choice(words) + random.choice(["", ",", "!", "  ", "?"]) for _ in range(random.randint(0, 14)))
+
+    texts = [make() for _ in range(1500)] + ["", "the a an", "   ", "!!!"]
+    for corpus in (texts, ["only one"], ["", ""], texts[:7] + ["with \x1d separator inside"] + texts[7:20]):
+        codes, offs, vocab = tokenize_corpus(corpus)
+        docs = [text_pipeline(t).split(" ") for t in corpus]
+        seen, ids = {}, []
+        for d in docs:
+            for w in d:
+                ids.append(seen.setdefault(w, len(seen)))
+        assert vocab == list(seen)
+        assert np.array_equal(codes, np.asarray(ids, dtype=np.int32))
+        assert np.array_equal(np.diff(offs), [len(d) for d in docs])
+    d = Document({i: t for i, t in enumerate(texts[:50])})
+    assert d.sample_docs_list == [text_pipeline(t).split(" ") for t in texts[:50]]
+    assert d.M == 50 and d.V == len(d.vocab_to_idx)

@@ -64,10 +64,10 @@ SIGNATURES = {
                                               _i64, _ptr]),
     "ttlda_beta_refresh_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr, _ptr, _i64,
                                               _ptr]),
-    "ttlda_mstep_slice_lambda_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr, _ptr,
-                                                    _i64, _ptr]),
-    "ttlda_mstep_slice_beta_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _i64, ctypes.c_int,
-                                                  _ptr, _ptr, _ptr, _i64, _ptr]),
+    "ttlda_mstep_slice_lambda_f64": (ctypes.c_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _ptr,
+                                                    _ptr, _i64, _ptr]),
+    "ttlda_mstep_slice_beta_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _i64, _i64, _f64, _ptr, _ptr, _i64, _ptr,
+                                                  ctypes.c_int, _ptr, _ptr, _ptr, _i64, _ptr]),
     "ttlda_elbo_tokens_f64": (ctypes.c_int, [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64,
                                              _ptr]),
     "ttlda_hyper_stats_f64": (ctypes.c_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
@@ -92,7 +92,7 @@ timing = None     # set to {} by bench.py: name -> [(start_event, end_event), ..
 # hand-written kernels launched by each entry point (CUB sort/RLE passes and memsets are not counted)
 KERNELS_PER_CALL = {
     "ttlda_dirichlet_expectation_f64": 1, "ttlda_dirichlet_expectation_1d_f64": 1,
-    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 2, "ttlda_csr_to_csc_block": 2, "ttlda_widen_i32": 1, "ttlda_validate_csr": 1,
+    "ttlda_bow_to_csr": 2, "ttlda_csr_to_csc": 4, "ttlda_csr_to_csc_block": 4, "ttlda_widen_i32": 1, "ttlda_validate_csr": 1,
     "ttlda_theta_refresh_f64": 2, "ttlda_estep_f64": 2, "ttlda_estep_hot_f64": 2, "ttlda_build_estream": 1, "ttlda_estep_fixed_point_f64": 2,
     "ttlda_sstats_csc_f64": 2, "ttlda_sstats_csc_windowed_f64": 0, "ttlda_sstats_atomic_f64": 1, "ttlda_sstats_csc_block_f64": 2, "ttlda_sstats_fold_f64": 1,
     "ttlda_mstep_f64": 4, "ttlda_mstep_online_f64": 4,
@@ -394,23 +394,26 @@ def _ptr_array(ptrs):
     return arr
 
 
-def mstep_slice_lambda(src_ptrs, src_row0, w0, n, K, eta, eB, lam, colsum_part, ws):
+def mstep_slice_lambda(src_ptrs, src_row0, w0, n, K, eta, eB, lam, colsum_part, ws, multicast=0):
     """Phase A of the sharded M-step on rows [w0, w0+n): src_ptrs = device addresses (ints) of the statistics tables to
-    sum in order — peer-mapped tables of every rank, or one locally reduced buffer."""
+    sum in order — peer-mapped tables of every rank, or one locally reduced buffer; multicast = their NVSwitch multicast
+    address (0: none), in which case the sum is read with multimem.ld_reduce."""
     ld = eB.shape[1]
     arr = _ptr_array(src_ptrs)
-    _call("ttlda_mstep_slice_lambda_f64", ctypes.cast(arr, ctypes.c_void_p), len(src_ptrs), int(src_row0), int(w0),
+    _call("ttlda_mstep_slice_lambda_f64", ctypes.cast(arr, ctypes.c_void_p), len(src_ptrs),
+          ctypes.c_void_p(int(multicast)) if multicast else None, int(src_row0), int(w0),
           int(n), int(K), ld, float(eta), _p(eB, f64), _p(lam, f64), _p(colsum_part, f64), _p(ws),
           ws.numel() * ws.element_size(), _stream())
 
 
-def mstep_slice_beta(colsum_parts, w0, n, K, eta, lam, dst_ptrs, add_colsum_term, colsum, partial, ws):
+def mstep_slice_beta(colsum_parts, w0, n, K, eta, lam, dst_ptrs, add_colsum_term, colsum, partial, ws, multicast=0):
     """Phase B: colsum_parts [nparts][ld] (rank order) -> colsum; exp(E[log beta]) rows [w0, w0+n) stored into every table
     of dst_ptrs (device addresses: this rank's table, or all ranks' through peer memory)."""
     nparts, ld = colsum_parts.shape
     arr = _ptr_array(dst_ptrs)
     _call("ttlda_mstep_slice_beta_f64", _p(colsum_parts, f64), nparts, int(w0), int(n), int(K), ld, float(eta),
-          _p(lam, f64), ctypes.cast(arr, ctypes.c_void_p), len(dst_ptrs), int(bool(add_colsum_term)), _p(colsum, f64),
+          _p(lam, f64), ctypes.cast(arr, ctypes.c_void_p), len(dst_ptrs),
+          ctypes.c_void_p(int(multicast)) if multicast else None, int(bool(add_colsum_term)), _p(colsum, f64),
           _p(partial, f64), _p(ws), ws.numel() * ws.element_size(), _stream())
 
 

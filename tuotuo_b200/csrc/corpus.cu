@@ -243,6 +243,218 @@ static int grid_1d(int64_t n)
     return (int)(g < 1 ? 1 : g);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Mirror of ONE document block by a hand-written counting sort (opt-in, TTLDA_CSC_TILES=1, for blocks of <= 65 535
+// documents; the CUB pair sort above is the default — see tile_path_applies for the measurement).
+//
+// A CSR block is already sorted by (document, word); its mirror is the same entries sorted by (word, document) — a
+// transpose.  Keys are bounded by V and distinct within a document, so the sort needs no comparisons; what it needs is,
+// for every entry, the number of EARLIER documents of the block that contain the same word (stability = documents
+// ascending within a word).  That rank is made order-free, hence fully parallel and deterministic:
+//   tiles   a CTA owns a tile of 32 consecutive documents; shared memory holds one 32-bit mask per word, bit i = "document
+//           i of the tile contains the word", built with atomicOr (an OR commutes: any arrival order gives the same mask);
+//           an entry's rank inside its tile is popc(mask & bits below its document).
+//   A hist  hist[tile][w] = popc(mask[w])                                                        (uint8)
+//   B scan  off[tile][w]  = sum over earlier tiles (uint16: a block holds < 65 536 documents); total[w]; colptr by an
+//           exclusive scan of the totals
+//   C place mirror position = colptr[w] + off[tile][w] + rank;  docidx / ccounts are written there, csr2csc[p] — one
+//           coalesced stream in CSR order — records it.
+// Vocabularies larger than the shared-memory mask array (58 112 words) are covered in word RANGES: the tile re-reads its
+// entries once per range.  Against the generic path (key packing, two 8-bit onesweep passes over (key, value) pairs, a
+// gather through the sorted permutation) there is no dependent random gather of 4-byte items and no 20-bytes-per-entry
+// scratch.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kTileDocs = 32;
+constexpr int kTileThreads = 512;                                // 16 warps: two documents of the tile per warp
+constexpr int64_t kTileRangeWords = (227 * 1024 / 4) / 16 * 16;  // words per range: one 32-bit mask each
+
+struct TilePlan {
+    int64_t tiles, vp, range_words;
+    int ranges;
+    size_t hist_b, off_b, total_b, total;
+};
+
+static TilePlan tile_plan(int64_t D, int64_t V)
+{
+    TilePlan t;
+    t.tiles = (D + kTileDocs - 1) / kTileDocs;
+    t.vp = (V + 15) / 16 * 16;
+    t.range_words = t.vp < kTileRangeWords ? (t.vp > 0 ? t.vp : 16) : kTileRangeWords;
+    t.ranges = (int)((t.vp + t.range_words - 1) / t.range_words);
+    if (t.ranges < 1) t.ranges = 1;
+    t.hist_b = align256((size_t)(t.tiles > 0 ? t.tiles : 1) * t.vp);
+    t.off_b = align256((size_t)(t.tiles > 0 ? t.tiles : 1) * t.vp * 2);
+    t.total_b = align256((size_t)(V + 1) * 4);
+    t.total = t.hist_b + t.off_b + t.total_b;
+    return t;
+}
+
+static bool tile_path_applies(int64_t D, int64_t V, int64_t nblocks)
+{
+    if (nblocks != 1 || D > 65535 || V < 1) return false;
+    // OPT-IN (TTLDA_CSC_TILES=1).  Same-box A/B of the streamed step at cfg3: 39.6 ms with this path against 36.3 ms
+    // with the CUB pair sort (cfg4: 56.1 vs 54.2): per tile the mask array is cleared and scanned densely — O(V) work
+    // for ~7k entries — and that outweighs the sort's two passes.  Kept because it is exact, allocation-light (0.3 GB
+    // instead of 20 bytes per entry) and the right starting point for a sparse-tile version.
+    const char* e = getenv("TTLDA_CSC_TILES");
+    if (!e || e[0] != '1') return false;
+    const TilePlan t = tile_plan(D, V);
+    return t.total <= ((size_t)3 << 30);  // scratch cap; beyond it the generic sort's 20 bytes per entry are smaller
+}
+
+// MODE 0: histogram (kernel A);  MODE 1: placement (kernel C).  One CTA per tile of 32 documents.
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads) csc_tile_kernel(
+    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts, int64_t D,
+    int64_t V, int64_t vp, int64_t range_words, int ranges, int64_t doc_base, int64_t pos_base,
+    uint8_t* __restrict__ hist, const uint16_t* __restrict__ off, const int64_t* __restrict__ colptr,
+    int32_t* __restrict__ docidx, int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
+{
+    extern __shared__ __align__(16) uint32_t tile_mask[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int kWarps = kTileThreads / 32;
+    const int64_t tile = blockIdx.x;
+    const int64_t d_lo = tile * kTileDocs;
+    const int nd = (int)((d_lo + kTileDocs < D) ? kTileDocs : D - d_lo);
+    for (int rg = 0; rg < ranges; ++rg) {
+        const int64_t lo = (int64_t)rg * range_words, hi = (lo + range_words < vp) ? lo + range_words : vp;
+        const int nw = (int)(hi - lo);
+        for (int i = threadIdx.x * 4; i < nw; i += kTileThreads * 4)
+            *reinterpret_cast<uint4*>(tile_mask + i) = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();
+        // which documents of the tile contain each word (an OR commutes: no ordering between lanes / warps needed)
+        for (int dl = warp; dl < nd; dl += kWarps) {
+            const int64_t b = rowptr[d_lo + dl] - pos_base, e = rowptr[d_lo + dl + 1] - pos_base;
+            for (int64_t p = b + lane; p < e; p += 32) {
+                const int64_t x = (int64_t)colidx[p] - lo;
+                if (x >= 0 && x < nw) atomicOr(tile_mask + x, 1u << dl);
+            }
+        }
+        __syncthreads();
+        if (MODE == 0) {
+            uint8_t* out = hist + tile * vp + lo;
+            for (int i = threadIdx.x * 4; i < nw; i += kTileThreads * 4) {
+                const uint4 m = *reinterpret_cast<const uint4*>(tile_mask + i);
+                *reinterpret_cast<uint32_t*>(out + i) = (uint32_t)__popc(m.x) | ((uint32_t)__popc(m.y) << 8) |
+                                                        ((uint32_t)__popc(m.z) << 16) | ((uint32_t)__popc(m.w) << 24);
+            }
+        } else {
+            for (int dl = warp; dl < nd; dl += kWarps) {
+                const int64_t b = rowptr[d_lo + dl] - pos_base, e = rowptr[d_lo + dl + 1] - pos_base;
+                const uint32_t below = (1u << dl) - 1u;
+                for (int64_t p = b + lane; p < e; p += 32) {
+                    const int w = colidx[p];
+                    const int64_t x = (int64_t)w - lo;
+                    if (x < 0 || x >= nw) continue;
+                    // documents before this one that contain w: inside the tile (mask), in earlier tiles (off), in the
+                    // block's words before w (colptr)
+                    const int64_t q = (colptr[w] - pos_base) + (int64_t)off[tile * vp + w] + __popc(tile_mask[x] & below);
+                    docidx[q] = (int32_t)(doc_base + d_lo + dl);
+                    if (ccounts) ccounts[q] = counts[p];
+                    if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + q);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// kernel B: per word, exclusive prefix of its tile counts (uint16) and its total
+__global__ void __launch_bounds__(256) csc_tile_scan_kernel(const uint8_t* __restrict__ hist, int64_t tiles, int64_t V,
+                                                            int64_t vp, uint16_t* __restrict__ off,
+                                                            uint32_t* __restrict__ total)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= V) return;
+    uint32_t run = 0;
+    int64_t t = 0;
+    for (; t + 8 <= tiles; t += 8) {
+        uint8_t c[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) c[u] = hist[(t + u) * vp + w];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            off[(t + u) * vp + w] = (uint16_t)run;
+            run += c[u];
+        }
+    }
+    for (; t < tiles; ++t) {
+        off[t * vp + w] = (uint16_t)run;
+        run += hist[t * vp + w];
+    }
+    total[w] = run;
+}
+
+// colptr[w] = pos_base + sum_{w' < w} total[w'], colptr[V] = pos_base + nnz; one CTA
+__global__ void __launch_bounds__(1024) csc_colptr_kernel(const uint32_t* __restrict__ total, int64_t V, int64_t pos_base,
+                                                          int64_t* __restrict__ colptr)
+{
+    __shared__ int64_t part[1024];
+    const int tid = threadIdx.x;
+    const int64_t per = (V + 1023) / 1024, b = (int64_t)tid * per, e = (b + per < V) ? b + per : V;
+    int64_t s = 0;
+    for (int64_t w = b; w < e; ++w) s += total[w];
+    part[tid] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan of the 1024 partials
+        const int64_t v = (tid >= o) ? part[tid - o] : 0;
+        __syncthreads();
+        part[tid] += v;
+        __syncthreads();
+    }
+    int64_t run = pos_base + part[tid] - s;
+    for (int64_t w = b; w < e; ++w) {
+        colptr[w] = run;
+        run += total[w];
+    }
+    if (tid == 1023) colptr[V] = pos_base + part[1023];
+}
+
+static int csr_to_csc_tiles(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
+                            int64_t nnz, int64_t doc_base, int64_t pos_base, int64_t* colptr, int32_t* docidx,
+                            int32_t* ccounts, uint32_t* csr2csc, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+{
+    const TilePlan t = tile_plan(D, V);
+    if ((int64_t)t.total > workspace_bytes) {
+        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)t.total);
+        return TTLDA_EWORKSPACE;
+    }
+    uint8_t* hist = (uint8_t*)workspace;
+    uint16_t* off = (uint16_t*)((char*)workspace + t.hist_b);
+    uint32_t* total = (uint32_t*)((char*)workspace + t.hist_b + t.off_b);
+    const size_t smem = (size_t)t.range_words * 4;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(csc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(csc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_tile)");
+        configured = true;
+    }
+    if (t.tiles > 0 && nnz > 0) {
+        const unsigned grid = (unsigned)t.tiles;
+        csc_tile_kernel<0><<<grid, kTileThreads, smem, s>>>(rowptr, colidx, counts, D, V, t.vp, t.range_words, t.ranges,
+                                                               doc_base, pos_base, hist, nullptr, nullptr, nullptr, nullptr,
+                                                               nullptr);
+        TTLDA_LAUNCH_CHECK("csc_tile_hist");
+        csc_tile_scan_kernel<<<(unsigned)((V + 255) / 256), 256, 0, s>>>(hist, t.tiles, V, t.vp, off, total);
+        TTLDA_LAUNCH_CHECK("csc_tile_scan");
+    } else {
+        cudaError_t e = cudaMemsetAsync(total, 0, (size_t)V * 4, s);
+        if (e != cudaSuccess) return cuda_fail(e, "memset totals");
+    }
+    csc_colptr_kernel<<<1, 1024, 0, s>>>(total, V, pos_base, colptr);
+    TTLDA_LAUNCH_CHECK("csc_colptr");
+    if (t.tiles > 0 && nnz > 0) {
+        const unsigned grid = (unsigned)t.tiles;
+        csc_tile_kernel<1><<<grid, kTileThreads, smem, s>>>(rowptr, colidx, counts, D, V, t.vp, t.range_words, t.ranges,
+                                                               doc_base, pos_base, nullptr, off, colptr, docidx, ccounts,
+                                                               csr2csc);
+        TTLDA_LAUNCH_CHECK("csc_tile_place");
+    }
+    return TTLDA_OK;
+}
+
 }  // namespace ttlda
 
 using namespace ttlda;
@@ -294,12 +506,16 @@ int ttlda_bow_to_csr(const int32_t* token_ids, const int64_t* doc_offsets, int64
 
 int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int64_t nblocks)
 {
-    (void)D;
-    if (nnz < 0 || V < 0 || nblocks < 1) return TTLDA_EINVAL;
+    if (nnz < 0 || V < 0 || D < 0 || nblocks < 1) return TTLDA_EINVAL;
     CscWs w;
     cudaError_t e = csc_layout(nnz, nblocks * V, nullptr, w);
     if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc workspace query");
-    return (int64_t)w.total;
+    size_t need = w.total;
+    if (tile_path_applies(D, V, nblocks)) {  // whichever path runs: the larger of the two layouts
+        const TilePlan t = tile_plan(D, V);
+        if (t.total > need) need = t.total;
+    }
+    return (int64_t)need;
 }
 
 static int csr_to_csc_impl(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
@@ -307,6 +523,9 @@ static int csr_to_csc_impl(const int64_t* rowptr, const int32_t* colidx, const i
                            int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc, void* workspace,
                            int64_t workspace_bytes, cudaStream_t s)
 {
+    if (tile_path_applies(D, V, nblocks))
+        return csr_to_csc_tiles(rowptr, colidx, counts, D, V, nnz, doc_base, pos_base, colptr, docidx, ccounts, csr2csc,
+                                workspace, workspace_bytes, s);
     const int64_t VV = nblocks * V;
     CscWs w;
     cudaError_t e = csc_layout(nnz, VV, (char*)workspace, w);

@@ -9,8 +9,8 @@
 // copies the H hottest rows into its shared memory once per launch (H = as many as fit in 227 KB: 289 rows of 800 B);
 // the document's nonzeros arrive in an "E-step stream" in which the hot ones come FIRST and carry their cache slot
 // instead of their word id (ttlda_build_estream, built once per corpus like the CSC mirror), so a warp runs a
-// homogeneous low-latency shared-memory phase and then the L2 phase over the remaining rows.  A row pointer is a
-// generic address (shared window or global), the traversal is otherwise the one of traverse.cuh.
+// homogeneous low-latency shared-memory phase (LDS.128) and then the L2 phase (LDG.128) over the remaining rows; which
+// of the two a sub-batch takes is warp-uniform.  The traversal is otherwise the one of traverse.cuh.
 //
 // Also different from doc_pass_kernel: the per-document epilogue stays in registers — the R lane groups' partial
 // accumulators are combined by log2(R) butterfly steps (every lane then holds the document's full sums for its own
@@ -63,9 +63,9 @@ __device__ __forceinline__ double2 ld_stream_f64x2(const double* p, uint64_t pol
     return v;
 }
 
-// E 16-byte loads through a GENERIC pointer (shared-memory cache slot or global table row), lane offset folded in
+// E 16-byte loads of a cached row (shared memory; lane offset folded into the pointer)
 template <int G, int E>
-__device__ __forceinline__ void load_generic(KSlice<G, E>& s, const double* rowg, bool last_ok)
+__device__ __forceinline__ void load_cached(KSlice<G, E>& s, const double* rowg, bool last_ok)
 {
 #pragma unroll
     for (int j = 0; j < E - 1; ++j) s.v[j] = *reinterpret_cast<const double2*>(rowg + 2 * G * j);
@@ -99,11 +99,18 @@ __global__ void __launch_bounds__(kHotThreads, 1) doc_pass_hot_kernel(const HotP
     }
     __syncthreads();
 
-    const double* cache_g = cache + 2 * g;  // generic address of this lane's first slice of slot 0
+    const double* cache_g = cache + 2 * g;  // this lane's first slice of slot 0 (shared memory)
     const double* table_g = P.eB + 2 * g;
-    auto row_of = [&](int idx) -> const double* {
-        return (idx < 0) ? cache_g + (uint32_t)(idx & 0x7fffffff) * (uint32_t)ld
-                         : table_g + (size_t)(uint32_t)idx * (uint32_t)ld;
+    // Sub-batch `sb` of a batch whose first `nh` entries are hot: all R rows cached -> LDS from the cache; otherwise all R
+    // rows come from the global table (a hot entry in a mixed sub-batch — at most one sub-batch per document — is read
+    // from the table through the word id its lane looked up when it loaded the entry).  Warp-uniform either way.
+    auto load_sub = [&](KSlice<G, E>& row, int raw, int wid, int sb, int nh) {
+        const int src = sb * R + r;
+        const int v_raw = __shfl_sync(0xffffffffu, raw, src), v_wid = __shfl_sync(0xffffffffu, wid, src);
+        if ((sb + 1) * R <= nh)
+            load_cached<G, E>(row, cache_g + (uint32_t)(v_raw & 0x7fffffff) * (uint32_t)ld, last_ok);
+        else
+            row.load_at(row_at(table_g, v_wid, ld), last_ok);
     };
 
     double tok_acc = 0., cnt_acc = 0.;
@@ -116,17 +123,19 @@ __global__ void __launch_bounds__(kHotThreads, 1) doc_pass_hot_kernel(const HotP
         acc.zero();
 
         // (row, count, mirror position) triples: 32 per coalesced load, fetched ONE batch ahead
-        int nx_w = 0, nx_c = 0, nx_pos = 0;
+        int nx_w = 0, nx_id = 0, nx_c = 0, nx_pos = 0;
         if (b + lane < e) {
             nx_w = ld_stream_s32(P.e_idx + b + lane, pol);
             nx_c = ld_stream_s32(P.e_cnt + b + lane, pol);
             if (P.ratio_csc) nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.e_pos) + b + lane, pol);
         }
+        nx_id = (nx_w < 0) ? P.hot_words[nx_w & 0x7fffffff] : nx_w;
+        int nx_nh = __popc(__ballot_sync(0xffffffffu, nx_w < 0));  // hot entries lead the document (and so the batch)
         KSlice<G, E> rowA, rowB;
-        if (b < e) load_generic<G, E>(rowA, row_of(__shfl_sync(0xffffffffu, nx_w, r)), last_ok);
+        if (b < e) load_sub(rowA, nx_w, nx_id, 0, nx_nh);
         for (int64_t n0 = b; n0 < e; n0 += 32) {
             const int cnt = (int)((e - n0 < 32) ? (e - n0) : 32);
-            const int my_w = nx_w, my_c = nx_c, my_pos = nx_pos;
+            const int my_w = nx_w, my_id = nx_id, my_c = nx_c, my_pos = nx_pos, my_nh = nx_nh;
             nx_w = 0;
             nx_c = 0;
             if (n0 + 32 + lane < e) {
@@ -134,6 +143,8 @@ __global__ void __launch_bounds__(kHotThreads, 1) doc_pass_hot_kernel(const HotP
                 nx_c = ld_stream_s32(P.e_cnt + n0 + 32 + lane, pol);
                 if (P.ratio_csc) nx_pos = ld_stream_s32(reinterpret_cast<const int32_t*>(P.e_pos) + n0 + 32 + lane, pol);
             }
+            nx_id = (nx_w < 0) ? P.hot_words[nx_w & 0x7fffffff] : nx_w;
+            nx_nh = __popc(__ballot_sync(0xffffffffu, nx_w < 0));
             const bool has_next = n0 + 32 < e;
             double my_p = 1.;
             auto body = [&](int s, const KSlice<G, E>& row) {
@@ -145,20 +156,20 @@ __global__ void __launch_bounds__(kHotThreads, 1) doc_pass_hot_kernel(const HotP
                 const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
                 if (lane / R == s) my_p = pv;
             };
-            // the row pipeline of traverse.cuh's walk_rows_carried, with generic row pointers
+            // the row pipeline of traverse.cuh's walk_rows_carried, rows from the cache or from the table
             const int nsub = (cnt + R - 1) / R;
             int s = 0;
             while (true) {
-                if (s + 1 < nsub) load_generic<G, E>(rowB, row_of(__shfl_sync(0xffffffffu, my_w, (s + 1) * R + r)), last_ok);
+                if (s + 1 < nsub) load_sub(rowB, my_w, my_id, s + 1, my_nh);
                 body(s, rowA);
                 if (++s >= nsub) {
-                    if (has_next) load_generic<G, E>(rowA, row_of(__shfl_sync(0xffffffffu, nx_w, r)), last_ok);
+                    if (has_next) load_sub(rowA, nx_w, nx_id, 0, nx_nh);
                     break;
                 }
                 if (s + 1 < nsub)
-                    load_generic<G, E>(rowA, row_of(__shfl_sync(0xffffffffu, my_w, (s + 1) * R + r)), last_ok);
+                    load_sub(rowA, my_w, my_id, s + 1, my_nh);
                 else if (has_next)
-                    load_generic<G, E>(rowA, row_of(__shfl_sync(0xffffffffu, nx_w, r)), last_ok);
+                    load_sub(rowA, nx_w, nx_id, 0, nx_nh);
                 body(s, rowB);
                 if (++s >= nsub) break;
             }

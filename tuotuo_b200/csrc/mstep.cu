@@ -138,7 +138,24 @@ constexpr int kMaxPeers = 8;  // ranks of one NVLink domain (one node)
 struct PeerTables {
     const double* src[kMaxPeers];
     double* dst[kMaxPeers];
+    const double* src_mc;  // multicast address of the statistics tables (NVSwitch), or NULL
+    double* dst_mc;        // multicast address of the exp(E[log beta]) tables, or NULL
 };
+
+// NVLink SHARP through the switch's multicast objects: ONE load returns the sum of the same address in every rank's
+// table (the reduction happens inside the NVSwitch: this rank's link carries the slice once, not once per peer), ONE
+// store lands in every rank's table.
+__device__ __forceinline__ double multimem_sum_f64(const double* mc)
+{
+    double v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void multimem_store_f64(double* mc, double v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
 
 __global__ void __launch_bounds__(256) mstep_slice_lambda_kernel(const PeerTables T, int nsrc, int64_t src_row0,
                                                                  int64_t w0, int64_t n, int K, int64_t ld, double eta,
@@ -163,12 +180,17 @@ __global__ void __launch_bounds__(256) mstep_slice_lambda_kernel(const PeerTable
                 if (k < K) {
                     // statistics of all ranks (lda_model.py:262 over every shard): the loads — NVLink round trips when the
                     // tables are peer-mapped — are all issued before the first add; the sum runs in rank order
-                    double v[kMaxPeers];
+                    double sum;
+                    if (T.src_mc) {
+                        sum = multimem_sum_f64(T.src_mc + is);  // summed in the switch
+                    } else {
+                        double v[kMaxPeers];
 #pragma unroll
-                    for (int i = 0; i < kMaxPeers; ++i) v[i] = (i < nsrc) ? T.src[i][is] : 0.;
-                    double sum = v[0];
+                        for (int i = 0; i < kMaxPeers; ++i) v[i] = (i < nsrc) ? T.src[i][is] : 0.;
+                        sum = v[0];
 #pragma unroll
-                    for (int i = 1; i < kMaxPeers; ++i) sum += v[i];  // + 0.0 for i >= nsrc: exact
+                        for (int i = 1; i < kMaxPeers; ++i) sum += v[i];  // + 0.0 for i >= nsrc: exact
+                    }
                     lam = eta + sum * eB[idx];  // lda_model.py:264 then :280
                 }
                 lambda[idx] = lam;
@@ -225,7 +247,11 @@ __global__ void __launch_bounds__(256) beta_slice_kernel(const double* __restric
             x = exp(e);
             t[0] += (eta - lam) * e + (lg - lg_eta);  // lda_model.py:40-41
         }
-        for (int d = 0; d < ndst; ++d) T.dst[d][base + i] = x;  // this rank's table and, over NVLink, every peer's
+        if (T.dst_mc) {
+            multimem_store_f64(T.dst_mc + base + i, x);  // one store, replicated by the switch into every rank's table
+        } else {
+            for (int d = 0; d < ndst; ++d) T.dst[d][base + i] = x;  // this rank's table and, over NVLink, every peer's
+        }
     }
     block_sum<1>(t, sm);
     if (threadIdx.x == 0) {
@@ -313,7 +339,8 @@ int ttlda_mstep_online_f64(const double* sstats, int64_t V, int64_t K, int64_t l
                         workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
-int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, int64_t src_row0, int64_t w0, int64_t n,
+int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, const double* src_multicast,
+                                 int64_t src_row0, int64_t w0, int64_t n,
                                  int64_t K, int64_t ld, double eta, const double* exp_elogbeta, double* lambda,
                                  double* colsum_part_out, void* workspace, int64_t workspace_bytes, void* stream)
 {
@@ -330,6 +357,7 @@ int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, 
         TTLDA_REQUIRE(src_tables[i], "NULL source table");
         T.src[i] = src_tables[i];
     }
+    T.src_mc = src_multicast;
     double* colpart = (double*)((char*)workspace + align256((size_t)reduce_ws_bytes()));
     int TX = 32;
     while (TX < 256 && TX < ld) TX *= 2;
@@ -346,8 +374,8 @@ int ttlda_mstep_slice_lambda_f64(const double* const* src_tables, int64_t nsrc, 
 
 int ttlda_mstep_slice_beta_f64(const double* colsum_parts, int64_t nparts, int64_t w0, int64_t n, int64_t K, int64_t ld,
                                double eta, const double* lambda, double* const* dst_tables, int64_t ndst,
-                               int add_colsum_term, double* colsum_out, double* partial_out, void* workspace,
-                               int64_t workspace_bytes, void* stream)
+                               double* dst_multicast, int add_colsum_term, double* colsum_out, double* partial_out,
+                               void* workspace, int64_t workspace_bytes, void* stream)
 {
     TTLDA_REQUIRE(colsum_parts && lambda && dst_tables && colsum_out && partial_out && workspace, "NULL pointer");
     TTLDA_REQUIRE(nparts >= 1 && nparts <= kColBlocks && ndst >= 1 && ndst <= kMaxPeers, "bad rank counts");
@@ -362,6 +390,7 @@ int ttlda_mstep_slice_beta_f64(const double* colsum_parts, int64_t nparts, int64
         TTLDA_REQUIRE(dst_tables[i], "NULL destination table");
         T.dst[i] = dst_tables[i];
     }
+    T.dst_mc = dst_multicast;
     char* ws = (char*)workspace;
     double* records = (double*)ws;
     double* psi_colsum = (double*)(ws + align256((size_t)reduce_ws_bytes()) + align256((size_t)kColBlocks * ld * sizeof(double)));

@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .text import text_pipeline
+from .text import text_pipeline, tokenize_corpus
 
 
 class Document:
@@ -25,41 +25,38 @@ class Document:
         else:
             self.num_doc_population = num_doc_population
 
-        # process_documents(sample=False)  (utils.py:89-130)
-        docs_list = []
-        length = 0
-        for _, v in sample_docs.items():
-            toks = text_pipeline(v).split(" ")  # an empty document yields [''] like the reference
-            docs_list.append(toks)
-            length += len(toks)
-        print(f"There are {len(docs_list)} documents in the dataset after processing")
+        # process_documents(sample=False) (utils.py:89-130) + get_vocab_from_docs / get_np_wct (utils.py:177-206): the
+        # text pipeline, tokenisation and first-appearance vocabulary ids for the WHOLE corpus in one vectorised pass
+        # (text.tokenize_corpus) instead of per-document Python loops
+        ids, offs, words = tokenize_corpus(list(sample_docs.values()))
+        length = int(offs[-1])
+        print(f"There are {len(offs) - 1} documents in the dataset after processing")
         if len(sample_docs):
             print(f"On average estimated document length is {round(length / len(sample_docs), 1)} "
                   f"words per document after processing")
-
-        # get_vocab_from_docs + get_np_wct: ids by first appearance scanning documents in order, tokens left to right
-        # (utils.py:177-206) — which is exactly pandas.factorize's code assignment, at C speed
-        import pandas as pd
-
-        offs = np.zeros(len(docs_list) + 1, dtype=np.int64)
-        np.cumsum([len(d) for d in docs_list], out=offs[1:])
-        flat = [w for d in docs_list for w in d]
-        if flat:
-            codes, uniques = pd.factorize(np.asarray(flat, dtype=object), sort=False)
-            ids = codes.astype(np.int32)
-            vocab = {w: j for j, w in enumerate(uniques.tolist())}
-        else:
-            ids, vocab = np.empty(0, dtype=np.int32), {}
+        vocab = {w: j for j, w in enumerate(words)}
         print(f"There are {len(vocab)} unique vocab in the corpus after processing")
 
-        self.sample_docs_list = docs_list
+        self._words = words
         self.vocab_to_idx = vocab
         self.idx_to_vocab = {v: k for k, v in vocab.items()}
         self.V = len(vocab)
-        self.M = len(docs_list)
+        self.M = len(offs) - 1
         self._token_ids, self._doc_offsets = ids, offs
         self._host_csr = None
         self._dev = {}
+
+    @property
+    def sample_docs_list(self):  # document.py:31 — list of token lists, materialised on demand
+        if getattr(self, "_docs_list", None) is None and getattr(self, "_words", None) is not None:
+            w = np.asarray(self._words, dtype=object)
+            ids, offs = np.asarray(self._token_ids), self._doc_offsets
+            self._docs_list = [w[ids[offs[d]:offs[d + 1]]].tolist() for d in range(len(offs) - 1)]
+        return getattr(self, "_docs_list", None)
+
+    @sample_docs_list.setter
+    def sample_docs_list(self, value):
+        self._docs_list = value
 
     # -- alternative constructors ---------------------------------------------------------------------------------------
     @classmethod

@@ -172,6 +172,12 @@ class LDASmoothed:
                 st.eB_pad = symm.empty((Vp, ld), dtype=f64, device=dev)
                 hs, hb = symm.rendezvous(st.sstats_pad, group), symm.rendezvous(st.eB_pad, group)
                 st.S_ptrs, st.eB_ptrs = [int(p) for p in hs.buffer_ptrs], [int(p) for p in hb.buffer_ptrs]
+                # NVSwitch multicast objects over the same tables (NVLink SHARP): in-switch sum / replicated store
+                use_mc = os.environ.get("TTLDA_MULTICAST", "1") == "1" and hs.has_multicast_support and hb.has_multicast_support
+                st.S_mc = int(hs.multicast_ptr) if use_mc else 0
+                st.eB_mc = int(hb.multicast_ptr) if use_mc else 0
+                if not (st.S_mc and st.eB_mc):
+                    st.S_mc = st.eB_mc = 0
                 if len(st.S_ptrs) != N or len(st.eB_ptrs) != N:
                     raise RuntimeError("symmetric memory rendezvous returned an unexpected number of peers")
                 st.symm = hs
@@ -439,13 +445,13 @@ class LDASmoothed:
             eta = float(self._eta_)
             src = st.S_ptrs if mode == "peer" else [st.S_slice.data_ptr()]
             nv.mstep_slice_lambda(src, st.w0 if mode == "peer" else 0, st.w0, st.wn, st.K, eta, st.eB, st.lam,
-                                  st.colpart_mine, st.ws_m)
+                                  st.colpart_mine, st.ws_m, multicast=st.S_mc if mode == "peer" else 0)
             # K column sums per rank: a 8K-byte exchange that is also the point after which no rank reads the others'
             # statistics any more (the next statistics pass may overwrite them)
             dist.all_gather_into_tensor(st.colparts, st.colpart_mine)
             dst = st.eB_ptrs if mode == "peer" else [st.eB.data_ptr()]
             nv.mstep_slice_beta(st.colparts, st.w0, st.wn, st.K, eta, st.lam, dst, dist.get_rank() == 0, st.colsum,
-                                st.part[2], st.ws_m)
+                                st.part[2], st.ws_m, multicast=st.eB_mc if mode == "peer" else 0)
             if mode == "peer":
                 st.symm.barrier(channel=1)  # all ranks' rows of exp(E[log beta]) have landed in this rank's table
             else:

@@ -67,3 +67,70 @@ def text_pipeline(s: str) -> str:  # utils.py:71-86 (same order of stages)
     s = remove_extra_whitespace_tabs(s)
     s = remove_stopwords(s)
     return s
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Whole-corpus form of the same pipeline: the reference runs `text_pipeline` once per document in
+# Python (utils.py:96-98) and then counts words with dict/list loops (utils.py:177-206), O(V*M).  Here the three
+# character-level stages run ONCE over all documents joined by a separator, the split into tokens is one C call, and
+# stop words are dropped by a vectorised mask over the token CODES — Python touches each distinct word once, not each
+# token.  Same tokens, same order, same first-appearance vocabulary ids as the per-document form
+# (tests/test_host_logic.py::test_corpus_tokenizer_equals_per_document_pipeline).
+# ----------------------------------------------------------------------------------------------------------------------
+_SEP = "\x1d"  # ASCII group separator: whitespace for `\s` (kept by stage 2), not punctuation (kept by stage 3)
+
+
+def tokenize_corpus(texts):
+    """texts: sequence of str.  Returns (codes int32[T], offsets int64[len(texts)+1], vocab list[str]) where
+    vocab[codes[offsets[d]:offsets[d+1]]] are the tokens `text_pipeline(texts[d]).split(' ')` yields (an empty document
+    yields the single token '' like the reference) and vocabulary ids are assigned by first appearance."""
+    import numpy as np
+    import pandas as pd
+
+    n = len(texts)
+    if n == 0:
+        return np.empty(0, dtype=np.int32), np.zeros(1, dtype=np.int64), []
+    if any(_SEP in t for t in texts):  # the separator occurs in the data: per-document path
+        docs = [text_pipeline(t).split(" ") for t in texts]
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum([len(d) for d in docs], out=offs[1:])
+        codes, uniques = pd.factorize(np.asarray([w for d in docs for w in d], dtype=object), sort=False)
+        return codes.astype(np.int32), offs, uniques.tolist()
+    joined = (" " + _SEP + " ").join(texts)
+    joined = remove_punctuation(remove_special_characters(remove_accented_chars(joined)))  # stages 1-3, char level
+    toks = np.asarray(joined.split(), dtype=object)  # stage 4 (whitespace runs) is what split() does
+    # NB: _SEP is whitespace for str.split() too, so the boundaries are recovered from a second, separator-only pass
+    sep_free = joined.split(_SEP)
+    if len(sep_free) != n:
+        raise AssertionError("document separator lost in the character-level stages")
+    lens_raw = np.fromiter((len(x.split()) for x in sep_free), dtype=np.int64, count=n)
+    codes, uniques = pd.factorize(toks, sort=False)
+    keep_word = np.fromiter((w.lower() not in STOPWORDS for w in uniques), dtype=bool, count=len(uniques))  # stage 5
+    keep = keep_word[codes] if len(codes) else np.zeros(0, dtype=bool)
+    doc_of = np.repeat(np.arange(n), lens_raw)
+    lens = np.bincount(doc_of[keep], minlength=n).astype(np.int64)
+    codes = codes[keep]
+    empty = lens == 0
+    if empty.any() or not keep_word.all():
+        # re-number by first appearance among the KEPT tokens, with '' for documents left without any token
+        words = uniques.to_numpy(dtype=object) if hasattr(uniques, "to_numpy") else np.asarray(uniques, dtype=object)
+        if empty.any():
+            blank = len(words)
+            words = np.append(words, "")
+            lens2 = np.where(empty, 1, lens)
+            offs = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(lens2, out=offs[1:])
+            out = np.empty(int(offs[-1]), dtype=np.int64)
+            fill = np.ones(int(offs[-1]), dtype=bool)
+            fill[offs[:-1][empty]] = False
+            out[fill] = codes
+            out[~fill] = blank
+            codes, lens = out, lens2
+        new_codes, first = pd.factorize(codes, sort=False)
+        vocab = [words[i] for i in first]
+        codes = new_codes
+    else:
+        vocab = uniques.tolist()
+    offs = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offs[1:])
+    return codes.astype(np.int32), offs, vocab
