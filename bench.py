@@ -373,12 +373,18 @@ def measure(ctx, name, doc, K, V, steps, warmup, *, sampling=False, e2e=False, f
     if world > 1:
         # every rank's own kernel time per step: the step runs at the pace of the slowest GPU (the ranks meet at the
         # statistics exchange), so the spread of this list is what weak scaling loses before any communication cost
-        mine = torch.tensor([sum(v for k, v in per_kernel.items() if k.startswith("ttlda_")), ms_local / steps],
+        cap = 1.0 if (clocks and "sw_power_cap" in clocks.get("reasons", [])) else 0.0
+        mine = torch.tensor([sum(v for k, v in per_kernel.items() if k.startswith("ttlda_")), ms_local / steps,
+                             float(clocks["sm_mhz"]) if clocks else 0.0, cap, float(c.nnz)],
                             dtype=torch.float64, device=dev)
         allr = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allr, mine)
         res["per_rank"] = {"kernel_ms": [round(float(t[0]), 3) for t in allr],
-                           "step_ms": [round(float(t[1]), 3) for t in allr]}
+                           "step_ms": [round(float(t[1]), 3) for t in allr],
+                           "sm_mhz_median": [float(t[2]) for t in allr],
+                           "sw_power_cap_seen": [bool(t[3]) for t in allr],
+                           "nnz": [int(t[4]) for t in allr],
+                           "note": "every rank samples its own GPU's clocks during the timed region"}
         work = st.sstats.clone()
         for _ in range(2):
             dist.all_reduce(work)

@@ -170,31 +170,48 @@ __global__ void __launch_bounds__(256) mstep_slice_lambda_kernel(const PeerTable
     double cs[kMaxJ];
 #pragma unroll
     for (int j = 0; j < kMaxJ; ++j) cs[j] = 0.;
-    for (int64_t wl = b0 + ty; wl < b1; wl += TY) {
+    // kRowIlp rows per trip: the cross-rank loads are NVLink round trips (~2 us), so each thread keeps
+    // kRowIlp * (columns per thread) * (1 multicast | nsrc peer) of them in flight before it touches the first result
+    constexpr int kRowIlp = 4;
+    for (int64_t wl0 = b0 + ty; wl0 < b1; wl0 += (int64_t)TY * kRowIlp) {
+        double sum[kRowIlp][kMaxJ];
 #pragma unroll
-        for (int j = 0; j < kMaxJ; ++j) {
-            const int k = tx + TX * j;
-            if (k < (int)ld) {
-                const int64_t is = (src_row0 + wl) * ld + k, idx = (w0 + wl) * ld + k;
-                double lam = 0.;
-                if (k < K) {
-                    // statistics of all ranks (lda_model.py:262 over every shard): the loads — NVLink round trips when the
-                    // tables are peer-mapped — are all issued before the first add; the sum runs in rank order
-                    double sum;
+        for (int u = 0; u < kRowIlp; ++u) {
+            const int64_t wl = wl0 + (int64_t)u * TY;
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) {
+                const int k = tx + TX * j;
+                sum[u][j] = 0.;
+                if (wl < b1 && k < K) {
+                    const int64_t is = (src_row0 + wl) * ld + k;
                     if (T.src_mc) {
-                        sum = multimem_sum_f64(T.src_mc + is);  // summed in the switch
+                        sum[u][j] = multimem_sum_f64(T.src_mc + is);  // statistics of all ranks, summed in the switch
                     } else {
+                        // ... or by plain loads through the peer pointers, in rank order (lda_model.py:262 over shards)
                         double v[kMaxPeers];
 #pragma unroll
                         for (int i = 0; i < kMaxPeers; ++i) v[i] = (i < nsrc) ? T.src[i][is] : 0.;
-                        sum = v[0];
+                        double a = v[0];
 #pragma unroll
-                        for (int i = 1; i < kMaxPeers; ++i) sum += v[i];  // + 0.0 for i >= nsrc: exact
+                        for (int i = 1; i < kMaxPeers; ++i) a += v[i];  // + 0.0 for i >= nsrc: exact
+                        sum[u][j] = a;
                     }
-                    lam = eta + sum * eB[idx];  // lda_model.py:264 then :280
                 }
-                lambda[idx] = lam;
-                cs[j] += lam;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kRowIlp; ++u) {
+            const int64_t wl = wl0 + (int64_t)u * TY;
+            if (wl >= b1) continue;
+#pragma unroll
+            for (int j = 0; j < kMaxJ; ++j) {
+                const int k = tx + TX * j;
+                if (k < (int)ld) {
+                    const int64_t idx = (w0 + wl) * ld + k;
+                    const double lam = (k < K) ? eta + sum[u][j] * eB[idx] : 0.;  // lda_model.py:264 then :280
+                    lambda[idx] = lam;
+                    cs[j] += lam;
+                }
             }
         }
     }
