@@ -274,7 +274,14 @@ def test_fit_readme_config(golden_dir, capsys):
     assert relerr(lda._alpha_, g["alpha"]) < 1e-9 and relerr(lda._eta_, g["eta"]) < 1e-9
     assert lda.M == 100 and lda.V == 40 and lda.train_doc.idx_to_vocab[0] == list(j["vocab_to_idx"])[0]
     lda.get_top_k_words(3)
-    assert "Topic 4" in capsys.readouterr().out
+    # lda_model.py:556-564: per topic, the 3 largest lambda entries in ASCENDING order of lambda, printed as "Top i -> word"
+    want = ""
+    for k in range(5):
+        want += f"Topic {k}\n"
+        for i, idx in enumerate(np.argsort(g["lam"][k, :])[-3:]):
+            want += f"Top {i + 1} -> {list(j['vocab_to_idx'])[idx]}\n"
+        want += "\n"
+    assert capsys.readouterr().out == want
     assert lda.fit(lda.train_doc, em_num_step=1) is None  # return_perplexities defaults to False
 
 
@@ -608,18 +615,66 @@ def test_sharded_mstep_slices_equal_full_mstep(nv, dev, K, V, N):
     assert abs(beta_total - float(part_ref[0].item())) <= 1e-12 * abs(float(part_ref[0].item()))
 
 
-@pytest.mark.parametrize("D,V,blocks", [(700, 900, 1), (2500, 70_000, 3), (40, 12, 2), (65, 58_200, 1)])
-def test_counting_sort_mirror_equals_sorted_mirror(monkeypatch, dev, D, V, blocks):
-    """The opt-in mirror by counting sort (32-document tiles, order-free bitmask ranks; TTLDA_CSC_TILES=1) builds the
-    same colptr / docidx / ccounts / csr2csc, bit for bit, as the default CUB-sort path — including a vocabulary that
-    needs two word ranges (V > 58 112) and a ragged last tile."""
+def _random_rows(seed, D, V, lo, hi, empty_every=0):
+    """CSR with `lo..hi` distinct, ascending word ids per document (uniform over the vocabulary), optional empty rows."""
+    rs = np.random.RandomState(seed)
+    rows = []
+    for d in range(D):
+        n = 0 if (empty_every and d % empty_every == 0) else int(rs.randint(lo, hi + 1))
+        rows.append(np.sort(rs.choice(V, size=min(n, V), replace=False)).astype(np.int32))
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    ci = np.concatenate(rows).astype(np.int32) if rows else np.zeros(0, np.int32)
+    ct = rs.randint(1, 9, size=len(ci)).astype(np.int32)
+    return rp, ci, ct
+
+
+@pytest.mark.parametrize("case", ["ragged", "three_blocks", "tiny", "one_cta_per_sm", "long_documents", "many_slices",
+                                  "long_slices", "vocabulary_too_large"])
+def test_slice_walk_mirror_equals_sorted_mirror(monkeypatch, dev, case):
+    """The default mirror — the hand-written counting sort of csrc/corpus.cu (per-slice in-order walk with 16-bit
+    shared-memory counters, scan over slices, placement) — builds the same colptr / docidx / ccounts / csr2csc, bit for
+    bit, as the generic CUB pair sort (TTLDA_CSC_WALK=0) and as a stable NumPy argsort: ragged and empty documents,
+    several document blocks, a vocabulary that leaves one CTA per SM (V > 56k), documents longer than one walk step
+    (> 512 entries), slices of more than one 512-document offsets chunk, and a vocabulary beyond the counter table
+    (V > 114 688: both settings run the generic path)."""
     from tuotuo_b200.corpus import DeviceCorpus
     from tuotuo_b200.synth import numpy_corpus
 
-    rp, ci, ct = numpy_corpus(300 + D, D, V, 8, 30, ragged=True)
+    blocks = 1
+    if case == "ragged":
+        D, V = 700, 900
+        rp, ci, ct = numpy_corpus(1000, D, V, 8, 30, ragged=True)
+    elif case == "three_blocks":
+        D, V, blocks = 2500, 70_000, 3
+        rp, ci, ct = numpy_corpus(2800, D, V, 8, 30, ragged=True)
+    elif case == "tiny":
+        D, V, blocks = 40, 12, 2
+        rp, ci, ct = numpy_corpus(340, D, V, 8, 30, ragged=True)
+    elif case == "one_cta_per_sm":
+        D, V = 65, 102_660
+        rp, ci, ct = _random_rows(5, D, V, 0, 400, empty_every=7)
+    elif case == "long_documents":
+        D, V = 90, 5_000
+        rp, ci, ct = _random_rows(6, D, V, 300, 1700, empty_every=11)
+    elif case == "many_slices":  # 296 slices of 68 documents; V = 50k as at cfg3
+        D, V = 20_000, 50_000
+        rp, ci, ct = _random_rows(7, D, V, 0, 12, empty_every=5)
+    elif case == "long_slices":  # 541 documents per slice: more than one 512-document offsets chunk
+        D, V = 160_000, 200
+        rs = np.random.RandomState(9)
+        n = rs.randint(0, 4, size=D)
+        start, stride = rs.randint(0, V, size=D), rs.randint(1, 50, size=D)
+        k = np.arange(3)[None, :]
+        w = np.sort(np.where(k < n[:, None], (start[:, None] + k * stride[:, None]) % V, V + k), axis=1)  # distinct per row
+        rp = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+        ci = w[w < V].astype(np.int32)
+        ct = rs.randint(1, 9, size=len(ci)).astype(np.int32)
+    else:
+        D, V = 300, 120_000
+        rp, ci, ct = _random_rows(8, D, V, 0, 40)
     out = []
-    for tiles in ("0", "1"):
-        monkeypatch.setenv("TTLDA_CSC_TILES", tiles)
+    for walk in ("0", "1"):
+        monkeypatch.setenv("TTLDA_CSC_WALK", walk)
         c = DeviceCorpus.from_host_csr(rp, ci, ct, V, dev)
         c.build_csc(blocks)
         out.append([t.clone() for t in (c.colptr, c.docidx[:c.nnz], c.ccounts[:c.nnz], c.csr2csc[:c.nnz])])
@@ -629,6 +684,47 @@ def test_counting_sort_mirror_equals_sorted_mirror(monkeypatch, dev, D, V, block
     bd = -(-D // blocks)
     order = np.argsort((docs // bd) * V + ci, kind="stable")
     assert np.array_equal(out[1][1].cpu().numpy(), docs[order])
+    assert np.array_equal(out[1][2].cpu().numpy(), ct[order])
+    assert np.array_equal(np.argsort(out[1][3].cpu().numpy().astype(np.int64), kind="stable"), order)
+
+
+def test_slice_walk_mirror_redoes_unordered_rows_with_atomics(monkeypatch, dev):
+    """The fast walk updates its 16-bit counters without atomics, which is only right for rows that hold every word once
+    (what np.nonzero gives the reference, what Document.from_csr checks).  It verifies that on the fly (strictly ascending
+    rows); a block that fails is redone by the atomic form of the same walk, so ANY row order / repetition still gets a
+    complete, in-bounds mirror: (a) rows that repeat words — the repeats take distinct ranks, every mirror slot holds the
+    right document; (b) unsorted rows of distinct words — bit-identical to the generic pair sort."""
+    from tuotuo_b200.corpus import DeviceCorpus
+
+    V, D = 30, 50
+    rs = np.random.RandomState(3)
+    rows = [np.sort(rs.randint(0, V, size=rs.randint(0, 25))).astype(np.int32) for _ in range(D)]  # with repeats
+    rp = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    ci = np.concatenate(rows).astype(np.int32)
+    ct = np.ones(len(ci), np.int32)
+    c = DeviceCorpus.from_host_csr(rp, ci, ct, V, dev)
+    c.build_csc(1)
+    docs = np.repeat(np.arange(D), np.diff(rp))
+    order = np.argsort(ci, kind="stable")
+    assert np.array_equal(c.docidx[:c.nnz].cpu().numpy(), docs[order])
+    pos = c.csr2csc[:c.nnz].cpu().numpy().astype(np.int64)
+    assert np.array_equal(np.sort(pos), np.arange(len(ci)))  # a permutation: every slot is written by one entry
+    assert np.array_equal(ci[np.argsort(pos)], ci[order])
+
+    V, D = 4000, 900
+    rp, ci, ct = _random_rows(12, D, V, 0, 700, empty_every=9)
+    for d in range(0, D, 3):  # every third row in random order
+        seg = slice(rp[d], rp[d + 1])
+        perm = rs.permutation(rp[d + 1] - rp[d])
+        ci[seg], ct[seg] = ci[seg][perm], ct[seg][perm]
+    out = []
+    for walk in ("0", "1"):
+        monkeypatch.setenv("TTLDA_CSC_WALK", walk)
+        c = DeviceCorpus.from_host_csr(rp, ci, ct, V, dev)
+        c.build_csc(2)
+        out.append([t.clone() for t in (c.colptr, c.docidx[:c.nnz], c.ccounts[:c.nnz], c.csr2csc[:c.nnz])])
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
 
 
 def test_cfg5_class_shapes_plan_the_windowed_pass():
@@ -965,6 +1061,39 @@ def test_edge_cases_vs_oracle(K, V, rows, fixed_point):
         assert abs(m._last_elbo - o.last_elbo) < 1e-11
     tol = 1e-8 if fixed_point else TOL_STATE
     assert relerr(m._gamma_, o.gamma) < tol and relerr(m._lambda_, o.lam) < tol
+
+
+@pytest.mark.parametrize("K", [66, 100, 128, 200, 500, 1000])
+def test_cp_async_ring_estep_is_exact(monkeypatch, K):
+    """TTLDA_RING=1: the E-step / ELBO pass with exp(E[log beta]) rows staged through the per-lane cp.async ring
+    (csrc/ring_gather.cuh) — lane groups of 8, 16 and 32, 3- and 4-stage rings; documents shorter than the look-ahead, ragged and empty
+    documents; same answers as the oracle, and bit-identical to the register-staged walk (same arithmetic order)."""
+    from tuotuo.document import Document
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import numpy_corpus
+
+    V = 900
+    rp, ci, ct = numpy_corpus(710 + K, 300, V, 25, 70, ragged=True)
+    # a few very short documents (1..5 distinct words: fewer sub-batches than ring stages) and an empty one
+    keep = np.ones(len(ci), bool)
+    for d, n in ((3, 1), (4, 2), (5, 5), (6, 0), (7, 9)):
+        keep[rp[d] + n:rp[d + 1]] = False
+    lens = np.add.reduceat(keep, rp[:-1]) * (np.diff(rp) > 0)
+    rp2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    ci, ct = ci[keep], ct[keep]
+    o = OracleLDA(K, engine="c")
+    po = o.fit(CSRCorpus(rp2, ci, ct, V), em_num_step=3)
+    base = LDASmoothed(K, verbose=False)
+    pb = base.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
+    monkeypatch.setenv("TTLDA_RING", "1")
+    m = LDASmoothed(K, verbose=False)
+    pg = m.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert relerr(pg, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
+    assert np.array_equal(m._gamma_, base._gamma_) and np.array_equal(m._lambda_, base._lambda_) and list(pg) == list(pb)
+    monkeypatch.setenv("TTLDA_FUSED_REFRESH", "1")  # MODE 1 kernel as well
+    m2 = LDASmoothed(K, verbose=False)
+    p2 = m2.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
+    assert relerr(p2, po) < TOL_PERP and relerr(m2._gamma_, o.gamma) < TOL_STATE
 
 
 @pytest.mark.parametrize("K", [70, 100, 128])

@@ -68,10 +68,17 @@ def main():
                 b = float(r[rd]) * UNIT[units[rd]] + float(r[wr]) * UNIT[units[wr]]
             except ValueError:
                 b = float("nan")
-            t = cur.setdefault(e, [0.0, 0.0, 0])
-            t[0] += b
+            t = cur.setdefault(e, [0.0, 0.0, 0, []])
+            t[3].append((r[kn].split("(")[0], b))
             t[1] += float(r[tm])
             t[2] += 1
+        for s_ in steps:  # a launch whose DRAM counters ncu reported as nan takes the mean of the same kernel's other
+            for t in s_.values():  # launches inside the same entry point call (the windows of one pass are alike)
+                for name, b in t[3]:
+                    if b != b:
+                        ok = [x for n_, x in t[3] if n_ == name and x == x]
+                        b = sum(ok) / len(ok) if ok else float("nan")
+                    t[0] += b
         def nlaunch(s):
             return sum(v[2] for v in s.values())
 

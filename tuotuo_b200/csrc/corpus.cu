@@ -223,213 +223,366 @@ static int grid_1d(int64_t n)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Mirror of ONE document block by a hand-written counting sort (opt-in, TTLDA_CSC_TILES=1, for blocks of <= 65 535
-// documents; the CUB pair sort above is the default — see tile_path_applies for the measurement).
+// Mirror of ONE document block by a hand-written, comparison-free, atomic-order-free counting sort: the "slice walk".
+// (Default for blocks whose vocabulary fits the shared-memory counter table, V <= ~115 000; TTLDA_CSC_WALK=0 or a larger
+// vocabulary selects the generic CUB pair sort above.)
 //
 // A CSR block is already sorted by (document, word); its mirror is the same entries sorted by (word, document) — a
-// transpose.  Keys are bounded by V and distinct within a document, so the sort needs no comparisons; what it needs is,
-// for every entry, the number of EARLIER documents of the block that contain the same word (stability = documents
-// ascending within a word).  That rank is made order-free, hence fully parallel and deterministic:
-//   tiles   a CTA owns a tile of 32 consecutive documents; shared memory holds one 32-bit mask per word, bit i = "document
-//           i of the tile contains the word", built with atomicOr (an OR commutes: any arrival order gives the same mask);
-//           an entry's rank inside its tile is popc(mask & bits below its document).
-//   A hist  hist[tile][w] = popc(mask[w])                                                        (uint8)
-//   B scan  off[tile][w]  = sum over earlier tiles (uint16: a block holds < 65 536 documents); total[w]; colptr by an
-//           exclusive scan of the totals
-//   C place mirror position = colptr[w] + off[tile][w] + rank;  docidx / ccounts are written there, csr2csc[p] — one
-//           coalesced stream in CSR order — records it.
-// Vocabularies larger than the shared-memory mask array (58 112 words) are covered in word RANGES: the tile re-reads its
-// entries once per range.  Against the generic path (key packing, two 8-bit onesweep passes over (key, value) pairs, a
-// gather through the sorted permutation) there is no dependent random gather of 4-byte items and no 20-bytes-per-entry
-// scratch.
+// transpose.  The mirror position of entry (d, w) is
+//     colptr[w] + #{documents d' < d of the block that contain w},
+// so what has to be computed per entry is a RANK among the earlier documents.  The block's documents are cut into S
+// contiguous slices (S = 148 or 296: one or two resident CTAs per SM); then
+//   1 walk   one CTA per slice keeps a 16-bit counter per word in shared memory (V * 2 bytes: 100 KB at V = 50k, 205 KB at
+//            V = 102 660) and visits its documents IN ORDER, one barrier per document: every entry takes its word's counter
+//            value as its rank inside the slice (rank[p], uint16) and increments it.  A document holds a word at most once,
+//            so inside a document no two threads meet on a counter and the ranks do not depend on thread order:
+//            deterministic.  (The increment is a shared-memory atomicAdd on the 32-bit word that holds two counters — so a
+//            malformed row with a repeated word still gets distinct, in-range ranks.)  The entries of the next kPF
+//            documents are already in registers when their turn comes.  At the end the counter table IS the slice's word
+//            histogram: hist[slice][w].
+//   2 scan   per word, the exclusive prefix of hist over the slices -> off[slice][w]; the totals -> colptr (one CTA).
+//   3 place  one warp per document: q = colptr[w] + off[slice(d)][w] + rank[p];  docidx[q] = d, (ccounts[q] = counts[p],)
+//            csr2csc[p] = q — csr2csc is one coalesced stream in CSR order.
+// Against the generic path (key packing, histogram, two 8-bit onesweep passes over (key, value) pairs, a dependent random
+// gather of doc ids through the sorted permutation: ~0.68 ms per 12.7M-entry block at cfg3) there is no pair sort, no
+// 20-bytes-per-entry scratch (2 bytes per entry + 6 bytes per (slice, word)), and the only serial part — the walk — is
+// ~200 barrier-separated steps per CTA.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kTileDocs = 32;
-constexpr int kTileThreads = 512;                                // 16 warps: two documents of the tile per warp
-constexpr int64_t kTileRangeWords = (227 * 1024 / 4) / 16 * 16;  // words per range: one 32-bit mask each
+constexpr int kWalkThreads = 512;  // entries of one document handled per step (longer documents loop)
+constexpr int kWalkPF = 8;         // documents whose entries are prefetched into registers ahead of the walk
+constexpr int kWalkSmemSM = 227 * 1024;
 
-struct TilePlan {
-    int64_t tiles, vp, range_words;
-    int ranges;
-    size_t hist_b, off_b, total_b, total;
+struct WalkPlan {
+    bool ok;
+    int64_t vp, dps, slices;
+    size_t smem, rank_b, hist_b, off_b, total_b, total;
 };
 
-static TilePlan tile_plan(int64_t D, int64_t V)
+static WalkPlan walk_plan(int64_t D, int64_t V, int64_t nnz)
 {
-    TilePlan t;
-    t.tiles = (D + kTileDocs - 1) / kTileDocs;
-    t.vp = (V + 15) / 16 * 16;
-    t.range_words = t.vp < kTileRangeWords ? (t.vp > 0 ? t.vp : 16) : kTileRangeWords;
-    t.ranges = (int)((t.vp + t.range_words - 1) / t.range_words);
-    if (t.ranges < 1) t.ranges = 1;
-    t.hist_b = align256((size_t)(t.tiles > 0 ? t.tiles : 1) * t.vp);
-    t.off_b = align256((size_t)(t.tiles > 0 ? t.tiles : 1) * t.vp * 2);
-    t.total_b = align256((size_t)(V + 1) * 4);
-    t.total = t.hist_b + t.off_b + t.total_b;
-    return t;
+    WalkPlan w{};
+    w.vp = (V + 7) / 8 * 8;  // counters are cleared / flushed as 16-byte vectors of eight
+    w.smem = (size_t)w.vp * 2;
+    // two CTAs per SM when two tables (+ 2 KB of static shared memory and the per-CTA reserve each) fit
+    const int per_sm = (2 * (w.smem + 3 * 1024) <= (size_t)kWalkSmemSM) ? 2 : 1;
+    const int64_t target = (int64_t)kSMs * per_sm;
+    w.dps = (D + target - 1) / target;
+    if (w.dps < 16) w.dps = 16;
+    w.slices = D > 0 ? (D + w.dps - 1) / w.dps : 1;
+    w.ok = V >= 1 && w.smem + 3 * 1024 <= (size_t)kWalkSmemSM && w.dps <= 65535 && nnz < ((int64_t)1 << 31) &&
+           target * w.vp < ((int64_t)1 << 32);
+    // buffer sizes from a bound on the slice count that is monotone in D (the workspace is sized for the largest block, a
+    // call may bring a smaller one: slices <= target and slices <= ceil(D / 16) always hold)
+    int64_t cap = (D + 15) / 16;
+    if (cap > target) cap = target;
+    if (cap < 1) cap = 1;
+    w.rank_b = align256((size_t)(nnz > 0 ? nnz : 1) * 2);
+    w.hist_b = align256((size_t)cap * w.vp * 2);
+    w.off_b = align256((size_t)cap * w.vp * 4);
+    w.total_b = align256((size_t)w.vp * 4 + 16);  // + the redo flag
+    w.total = w.rank_b + w.hist_b + w.off_b + w.total_b;
+    return w;
 }
 
-static bool tile_path_applies(int64_t D, int64_t V, int64_t nblocks)
+static bool walk_path_applies(int64_t D, int64_t V, int64_t nnz, int64_t nblocks)
 {
-    if (nblocks != 1 || D > 65535 || V < 1) return false;
-    // OPT-IN (TTLDA_CSC_TILES=1).  Same-box A/B of the streamed step at cfg3: 39.6 ms with this path against 36.3 ms
-    // with the CUB pair sort (cfg4: 56.1 vs 54.2): per tile the mask array is cleared and scanned densely — O(V) work
-    // for ~7k entries — and that outweighs the sort's two passes.  Kept because it is exact, allocation-light (0.3 GB
-    // instead of 20 bytes per entry) and the right starting point for a sparse-tile version.
-    const char* e = getenv("TTLDA_CSC_TILES");
-    if (!e || e[0] != '1') return false;
-    const TilePlan t = tile_plan(D, V);
-    return t.total <= ((size_t)3 << 30);  // scratch cap; beyond it the generic sort's 20 bytes per entry are smaller
+    if (nblocks != 1) return false;
+    const char* e = getenv("TTLDA_CSC_WALK");
+    if (e && e[0] == '0') return false;
+    return walk_plan(D, V, nnz).ok;
 }
 
-// MODE 0: histogram (kernel A);  MODE 1: placement (kernel C).  One CTA per tile of 32 documents.
-template <int MODE>
-__global__ void __launch_bounds__(kTileThreads) csc_tile_kernel(
-    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts, int64_t D,
-    int64_t V, int64_t vp, int64_t range_words, int ranges, int64_t doc_base, int64_t pos_base,
-    uint8_t* __restrict__ hist, const uint16_t* __restrict__ off, const int64_t* __restrict__ colptr,
-    int32_t* __restrict__ docidx, int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
+// 1: the walk.  rank[p] = documents of the slice before p's that contain p's word;  hist[slice][*] = the slice's word counts.
+// Also fills docidx[.] of the slice's entry range with a valid document id, so that whatever a malformed corpus makes of
+// the placement (3), no slot of the mirror is left holding garbage that a gather would follow.
+//
+// ATOMIC = false (the fast form): the counter update is a plain 16-bit LDS + STS — a shared-memory atomic costs ~2 cycles
+// per LANE on this part (64 per warp instruction) and made the walk 3x slower than the rest of the sort.  That is only
+// right when no document repeats a word, which holds for every row the reference can produce (np.nonzero) and is what
+// Document.from_csr checks; the kernel checks it again on the fly (each entry against its predecessor: strictly ascending)
+// and raises *redo if a row fails.  ATOMIC = true is the same walk with atomicAdd on the 32-bit word that holds two
+// counters: launched right behind the fast form, it returns at once unless *redo is set, and then recomputes the block's
+// ranks and histograms correctly for ANY row order / repetition (distinct, in-range ranks).
+template <bool ATOMIC>
+__global__ void __launch_bounds__(kWalkThreads) csc_walk_kernel(const int64_t* __restrict__ rowptr,
+                                                                const int32_t* __restrict__ colidx, int64_t D, int64_t V,
+                                                                int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base,
+                                                                uint16_t* __restrict__ rank, uint32_t* __restrict__ hist32,
+                                                                int32_t* __restrict__ docidx, int32_t* __restrict__ redo)
 {
-    extern __shared__ __align__(16) uint32_t tile_mask[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int kWarps = kTileThreads / 32;
-    const int64_t tile = blockIdx.x;
-    const int64_t d_lo = tile * kTileDocs;
-    const int nd = (int)((d_lo + kTileDocs < D) ? kTileDocs : D - d_lo);
-    for (int rg = 0; rg < ranges; ++rg) {
-        const int64_t lo = (int64_t)rg * range_words, hi = (lo + range_words < vp) ? lo + range_words : vp;
-        const int nw = (int)(hi - lo);
-        for (int i = threadIdx.x * 4; i < nw; i += kTileThreads * 4)
-            *reinterpret_cast<uint4*>(tile_mask + i) = make_uint4(0u, 0u, 0u, 0u);
-        __syncthreads();
-        // which documents of the tile contain each word (an OR commutes: no ordering between lanes / warps needed)
-        for (int dl = warp; dl < nd; dl += kWarps) {
-            const int64_t b = rowptr[d_lo + dl] - pos_base, e = rowptr[d_lo + dl + 1] - pos_base;
-            for (int64_t p = b + lane; p < e; p += 32) {
-                const int64_t x = (int64_t)colidx[p] - lo;
-                if (x >= 0 && x < nw) atomicOr(tile_mask + x, 1u << dl);
+    extern __shared__ __align__(16) uint32_t walk_tab[];  // vp / 2 words, two 16-bit counters each
+    __shared__ int s_off[kWalkThreads + 1];               // entry offsets of up to kWalkThreads documents
+    if (ATOMIC && *redo == 0) return;
+    const int t = threadIdx.x;
+    const int half = (int)(vp >> 1);
+    const int64_t d_lo = (int64_t)blockIdx.x * dps;
+    const int64_t d_hi = (d_lo + dps < D) ? d_lo + dps : D;
+    for (int i = t * 4; i < half; i += kWalkThreads * 4) *reinterpret_cast<uint4*>(walk_tab + i) = make_uint4(0u, 0u, 0u, 0u);
+    uint16_t* tab16 = reinterpret_cast<uint16_t*>(walk_tab);
+    bool unordered = false;
+
+    auto place = [&](int w, int64_t p) {
+        if (!ATOMIC) docidx[p] = (int32_t)doc_base;
+        unsigned r = 0;
+        if ((unsigned)w < (unsigned)V) {
+            if (ATOMIC) {
+                const unsigned sh = (unsigned)(w & 1) << 4;
+                r = atomicAdd(walk_tab + (w >> 1), 1u << sh) >> sh;
+            } else {
+                r = tab16[w];
+                tab16[w] = (uint16_t)(r + 1);
             }
         }
+        rank[p] = (uint16_t)r;
+    };
+
+    for (int64_t c0 = d_lo; c0 < d_hi; c0 += kWalkThreads) {
+        const int n = (int)((d_hi - c0 < kWalkThreads) ? d_hi - c0 : kWalkThreads);
+        __syncthreads();  // the table is cleared / the previous chunk's offsets are no longer read
+        const int64_t base = rowptr[c0] - pos_base;
+        for (int i = t; i <= n; i += kWalkThreads) s_off[i] = (int)(rowptr[c0 + i] - pos_base - base);
         __syncthreads();
-        if (MODE == 0) {
-            uint8_t* out = hist + tile * vp + lo;
-            for (int i = threadIdx.x * 4; i < nw; i += kTileThreads * 4) {
-                const uint4 m = *reinterpret_cast<const uint4*>(tile_mask + i);
-                *reinterpret_cast<uint32_t*>(out + i) = (uint32_t)__popc(m.x) | ((uint32_t)__popc(m.y) << 8) |
-                                                        ((uint32_t)__popc(m.z) << 16) | ((uint32_t)__popc(m.w) << 24);
+        const int32_t* ci = colidx + base;
+        int wq[kWalkPF], pq[kWalkPF];  // this thread's entry of the next kWalkPF documents, and the entry before it
+#pragma unroll
+        for (int u = 0; u < kWalkPF; ++u) {
+            wq[u] = -1;
+            pq[u] = -1;
+            if (u < n && s_off[u] + t < s_off[u + 1]) {
+                wq[u] = ci[s_off[u] + t];
+                if (!ATOMIC && t > 0) pq[u] = ci[s_off[u] + t - 1];
             }
-        } else {
-            for (int dl = warp; dl < nd; dl += kWarps) {
-                const int64_t b = rowptr[d_lo + dl] - pos_base, e = rowptr[d_lo + dl + 1] - pos_base;
-                const uint32_t below = (1u << dl) - 1u;
-                for (int64_t p = b + lane; p < e; p += 32) {
-                    const int w = colidx[p];
-                    const int64_t x = (int64_t)w - lo;
-                    if (x < 0 || x >= nw) continue;
-                    // documents before this one that contain w: inside the tile (mask), in earlier tiles (off), in the
-                    // block's words before w (colptr)
-                    const int64_t q = (colptr[w] - pos_base) + (int64_t)off[tile * vp + w] + __popc(tile_mask[x] & below);
-                    docidx[q] = (int32_t)(doc_base + d_lo + dl);
-                    if (ccounts) ccounts[q] = counts[p];
-                    if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + q);
+        }
+        for (int j0 = 0; j0 < n; j0 += kWalkPF) {
+#pragma unroll
+            for (int u = 0; u < kWalkPF; ++u) {
+                const int j = j0 + u;
+                if (j < n) {  // CTA-uniform
+                    const int b = s_off[j], e = s_off[j + 1];
+                    const int w = wq[u], wp = pq[u];
+                    const bool mine = b + t < e;
+                    wq[u] = -1;
+                    pq[u] = -1;
+                    if (j + kWalkPF < n && s_off[j + kWalkPF] + t < s_off[j + kWalkPF + 1]) {
+                        wq[u] = ci[s_off[j + kWalkPF] + t];
+                        if (!ATOMIC && t > 0) pq[u] = ci[s_off[j + kWalkPF] + t - 1];
+                    }
+                    if (mine) {
+                        unordered |= (w <= wp);  // wp = -1 for a document's first entry; ids are >= 0 (else flagged later)
+                        place(w, base + b + t);
+                    }
+                    for (int i = b + t + kWalkThreads; i < e; i += kWalkThreads) {  // long documents
+                        const int wl = ci[i];
+                        unordered |= (wl <= ci[i - 1]);
+                        place(wl, base + i);
+                    }
+                    __syncthreads();  // document j is counted before document j + 1 reads the counters
                 }
             }
         }
-        __syncthreads();
     }
+    if (!ATOMIC && unordered) *redo = 1;
+    __syncthreads();
+    uint32_t* out = hist32 + (size_t)blockIdx.x * half;
+    for (int i = t * 4; i < half; i += kWalkThreads * 4)
+        *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(walk_tab + i);
 }
 
-// kernel B: per word, exclusive prefix of its tile counts (uint16) and its total
-__global__ void __launch_bounds__(256) csc_tile_scan_kernel(const uint8_t* __restrict__ hist, int64_t tiles, int64_t V,
-                                                            int64_t vp, uint16_t* __restrict__ off,
-                                                            uint32_t* __restrict__ total)
+// 2: per word, exclusive prefix of the slice counts and the total; one thread per PAIR of words (the packed counters)
+__global__ void __launch_bounds__(256) csc_walk_scan_kernel(const uint32_t* __restrict__ hist32, int64_t slices, int64_t vp,
+                                                            uint32_t* __restrict__ off, uint32_t* __restrict__ total)
 {
-    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= V) return;
-    uint32_t run = 0;
-    int64_t t = 0;
-    for (; t + 8 <= tiles; t += 8) {
-        uint8_t c[8];
+    const int64_t half = vp >> 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint32_t r0 = 0, r1 = 0;
+    int64_t s = 0;
+    for (; s + 8 <= slices; s += 8) {
+        uint32_t h[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) c[u] = hist[(t + u) * vp + w];
+        for (int u = 0; u < 8; ++u) h[u] = hist32[(s + u) * half + i];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            off[(t + u) * vp + w] = (uint16_t)run;
-            run += c[u];
+            *reinterpret_cast<uint2*>(off + (s + u) * vp + 2 * i) = make_uint2(r0, r1);
+            r0 += h[u] & 0xffffu;
+            r1 += h[u] >> 16;
         }
     }
-    for (; t < tiles; ++t) {
-        off[t * vp + w] = (uint16_t)run;
-        run += hist[t * vp + w];
+    for (; s < slices; ++s) {
+        const uint32_t h = hist32[s * half + i];
+        *reinterpret_cast<uint2*>(off + s * vp + 2 * i) = make_uint2(r0, r1);
+        r0 += h & 0xffffu;
+        r1 += h >> 16;
     }
-    total[w] = run;
+    *reinterpret_cast<uint2*>(total + 2 * i) = make_uint2(r0, r1);
 }
 
-// colptr[w] = pos_base + sum_{w' < w} total[w'], colptr[V] = pos_base + nnz; one CTA
+// colptr[w] = pos_base + sum_{w' < w} total[w'] (never beyond the block: pos_base + nnz), colptr[V] = pos_base + nnz.
+// One CTA scans the totals 1024 at a time (coalesced loads, warp shuffles, a running carry).
 __global__ void __launch_bounds__(1024) csc_colptr_kernel(const uint32_t* __restrict__ total, int64_t V, int64_t pos_base,
-                                                          int64_t* __restrict__ colptr)
+                                                          int64_t nnz, int64_t* __restrict__ colptr)
 {
-    __shared__ int64_t part[1024];
-    const int tid = threadIdx.x;
-    const int64_t per = (V + 1023) / 1024, b = (int64_t)tid * per, e = (b + per < V) ? b + per : V;
-    int64_t s = 0;
-    for (int64_t w = b; w < e; ++w) s += total[w];
-    part[tid] = s;
+    __shared__ int64_t wsum[32];
+    __shared__ int64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan of the 1024 partials
-        const int64_t v = (tid >= o) ? part[tid - o] : 0;
+    for (int64_t c0 = 0; c0 < V; c0 += 1024) {
+        const int64_t w = c0 + tid;
+        const int64_t v = (w < V) ? (int64_t)total[w] : 0;
+        int64_t x = v;  // inclusive scan inside the warp
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
         __syncthreads();
-        part[tid] += v;
+        if (warp == 0) {
+            int64_t s = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            wsum[lane] = s;  // inclusive over the warps
+        }
+        __syncthreads();
+        const int64_t carry = carry_s;
+        const int64_t excl = carry + (warp ? wsum[warp - 1] : 0) + (x - v);
+        if (w < V) colptr[w] = pos_base + (excl < nnz ? excl : nnz);
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + wsum[31];
         __syncthreads();
     }
-    int64_t run = pos_base + part[tid] - s;
-    for (int64_t w = b; w < e; ++w) {
-        colptr[w] = run;
-        run += total[w];
-    }
-    if (tid == 1023) colptr[V] = pos_base + part[1023];
+    if (tid == 0) colptr[V] = pos_base + nnz;
 }
 
-static int csr_to_csc_tiles(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
-                            int64_t nnz, int64_t doc_base, int64_t pos_base, int64_t* colptr, int32_t* docidx,
-                            int32_t* ccounts, uint32_t* csr2csc, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+// 3: placement, one warp per document
+__global__ void __launch_bounds__(256) csc_walk_place_kernel(const int64_t* __restrict__ rowptr,
+                                                             const int32_t* __restrict__ colidx,
+                                                             const int32_t* __restrict__ counts, int64_t D, int64_t V,
+                                                             int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base,
+                                                             int64_t nnz, const uint16_t* __restrict__ rank,
+                                                             const uint32_t* __restrict__ off,
+                                                             const int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
+                                                             int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
 {
-    const TilePlan t = tile_plan(D, V);
-    if ((int64_t)t.total > workspace_bytes) {
-        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)t.total);
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t d = warp0; d < D; d += nwarps) {
+        const int64_t b = rowptr[d] - pos_base, e = rowptr[d + 1] - pos_base;
+        const uint32_t* offs = off + (d / dps) * vp;
+        for (int64_t p = b + lane; p < e; p += 32) {
+            const int w = colidx[p];
+            int64_t q = p;  // a word id outside [0, V) (malformed, and not sanitised by the caller): stay in bounds
+            if ((unsigned)w < (unsigned)V) {
+                q = (colptr[w] - pos_base) + (int64_t)offs[w] + (int64_t)rank[p];
+                if (q >= nnz) q = nnz - 1;  // only a corpus that overflows a 16-bit counter (> 65 535 repeats) gets here
+                docidx[q] = (int32_t)(doc_base + d);
+                if (ccounts) ccounts[q] = counts[p];
+            }
+            if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + q);
+        }
+    }
+}
+
+// 3, when a 32-bit entry per word fits shared memory (V <= ~57 000): one CTA per SLICE first stages the slice's placement
+// bases colptr[w] + off[slice][w] with coalesced loads (the generic form above fetches them with two dependent random
+// 4/8-byte reads per entry: a 32-byte sector each), then places its documents' entries from shared memory.
+constexpr int kPlaceThreads = 1024;
+__global__ void __launch_bounds__(kPlaceThreads) csc_walk_place_slice_kernel(
+    const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts, int64_t D,
+    int64_t V, int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base, int64_t nnz, const uint16_t* __restrict__ rank,
+    const uint32_t* __restrict__ off, const int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
+    int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
+{
+    extern __shared__ __align__(16) uint32_t place_base[];  // vp words
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const uint32_t* offs = off + (size_t)blockIdx.x * vp;
+    for (int64_t w = t; w < V; w += kPlaceThreads) place_base[w] = (uint32_t)(colptr[w] - pos_base) + offs[w];
+    __syncthreads();
+    const int64_t d_lo = (int64_t)blockIdx.x * dps;
+    const int64_t d_hi = (d_lo + dps < D) ? d_lo + dps : D;
+    for (int64_t d = d_lo + warp; d < d_hi; d += kPlaceThreads / 32) {
+        const int64_t b = rowptr[d] - pos_base, e = rowptr[d + 1] - pos_base;
+        for (int64_t p = b + lane; p < e; p += 32) {
+            const int w = colidx[p];
+            int64_t q = p;  // a word id outside [0, V): stay in bounds (see the generic form)
+            if ((unsigned)w < (unsigned)V) {
+                q = (int64_t)place_base[w] + (int64_t)rank[p];
+                if (q >= nnz) q = nnz - 1;
+                docidx[q] = (int32_t)(doc_base + d);
+                if (ccounts) ccounts[q] = counts[p];
+            }
+            if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + q);
+        }
+    }
+}
+
+static int csr_to_csc_walk(const int64_t* rowptr, const int32_t* colidx, const int32_t* counts, int64_t D, int64_t V,
+                           int64_t nnz, int64_t doc_base, int64_t pos_base, int64_t* colptr, int32_t* docidx,
+                           int32_t* ccounts, uint32_t* csr2csc, void* workspace, int64_t workspace_bytes, cudaStream_t s)
+{
+    const WalkPlan w = walk_plan(D, V, nnz);
+    if ((int64_t)w.total > workspace_bytes) {
+        set_error("csr_to_csc: workspace %lld < %lld", (long long)workspace_bytes, (long long)w.total);
         return TTLDA_EWORKSPACE;
     }
-    uint8_t* hist = (uint8_t*)workspace;
-    uint16_t* off = (uint16_t*)((char*)workspace + t.hist_b);
-    uint32_t* total = (uint32_t*)((char*)workspace + t.hist_b + t.off_b);
-    const size_t smem = (size_t)t.range_words * 4;
+    char* base = (char*)workspace;
+    uint16_t* rank = (uint16_t*)base;
+    uint32_t* hist32 = (uint32_t*)(base + w.rank_b);
+    uint32_t* off = (uint32_t*)(base + w.rank_b + w.hist_b);
+    uint32_t* total = (uint32_t*)(base + w.rank_b + w.hist_b + w.off_b);
+    int32_t* redo = (int32_t*)(total + w.vp);  // "a row repeats or misorders words: redo the walk with atomics"
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(csc_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(csc_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kWalkSmemSM - 3 * 1024);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(csc_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_tile)");
+            e = cudaFuncSetAttribute(csc_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kWalkSmemSM - 3 * 1024);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_walk)");
         configured = true;
     }
-    if (t.tiles > 0 && nnz > 0) {
-        const unsigned grid = (unsigned)t.tiles;
-        csc_tile_kernel<0><<<grid, kTileThreads, smem, s>>>(rowptr, colidx, counts, D, V, t.vp, t.range_words, t.ranges,
-                                                               doc_base, pos_base, hist, nullptr, nullptr, nullptr, nullptr,
-                                                               nullptr);
-        TTLDA_LAUNCH_CHECK("csc_tile_hist");
-        csc_tile_scan_kernel<<<(unsigned)((V + 255) / 256), 256, 0, s>>>(hist, t.tiles, V, t.vp, off, total);
-        TTLDA_LAUNCH_CHECK("csc_tile_scan");
+    if (D > 0 && nnz > 0) {
+        cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int32_t), s);
+        if (e != cudaSuccess) return cuda_fail(e, "memset redo flag");
+        csc_walk_kernel<false><<<(unsigned)w.slices, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.dps, doc_base,
+                                                                                  pos_base, rank, hist32, docidx, redo);
+        TTLDA_LAUNCH_CHECK("csc_walk");
+        csc_walk_kernel<true><<<(unsigned)w.slices, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.dps, doc_base,
+                                                                                 pos_base, rank, hist32, docidx, redo);
+        TTLDA_LAUNCH_CHECK("csc_walk (atomic redo)");
+        csc_walk_scan_kernel<<<(unsigned)((w.vp / 2 + 255) / 256), 256, 0, s>>>(hist32, w.slices, w.vp, off, total);
+        TTLDA_LAUNCH_CHECK("csc_walk_scan");
     } else {
-        cudaError_t e = cudaMemsetAsync(total, 0, (size_t)V * 4, s);
+        cudaError_t e = cudaMemsetAsync(total, 0, (size_t)w.vp * 4, s);
         if (e != cudaSuccess) return cuda_fail(e, "memset totals");
     }
-    csc_colptr_kernel<<<1, 1024, 0, s>>>(total, V, pos_base, colptr);
+    csc_colptr_kernel<<<1, 1024, 0, s>>>(total, V, pos_base, nnz, colptr);
     TTLDA_LAUNCH_CHECK("csc_colptr");
-    if (t.tiles > 0 && nnz > 0) {
-        const unsigned grid = (unsigned)t.tiles;
-        csc_tile_kernel<1><<<grid, kTileThreads, smem, s>>>(rowptr, colidx, counts, D, V, t.vp, t.range_words, t.ranges,
-                                                               doc_base, pos_base, nullptr, off, colptr, docidx, ccounts,
-                                                               csr2csc);
-        TTLDA_LAUNCH_CHECK("csc_tile_place");
+    if (D > 0 && nnz > 0) {
+        const size_t place_smem = (size_t)w.vp * 4;
+        // (staging V bases per slice only pays when the slice has entries to place with them)
+        if (place_smem + 3 * 1024 <= (size_t)kWalkSmemSM && nnz / w.slices >= w.vp / 4) {
+            static bool place_configured = false;
+            if (!place_configured) {
+                cudaError_t e = cudaFuncSetAttribute(csc_walk_place_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     kWalkSmemSM - 3 * 1024);
+                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_walk_place_slice)");
+                place_configured = true;
+            }
+            csc_walk_place_slice_kernel<<<(unsigned)w.slices, kPlaceThreads, place_smem, s>>>(
+                rowptr, colidx, counts, D, V, w.vp, w.dps, doc_base, pos_base, nnz, rank, off, colptr, docidx, ccounts,
+                csr2csc);
+        } else {
+            csc_walk_place_kernel<<<grid_for_warps(D, 8, 16), 256, 0, s>>>(rowptr, colidx, counts, D, V, w.vp, w.dps,
+                                                                           doc_base, pos_base, nnz, rank, off, colptr,
+                                                                           docidx, ccounts, csr2csc);
+        }
+        TTLDA_LAUNCH_CHECK("csc_walk_place");
     }
     return TTLDA_OK;
 }
@@ -490,9 +643,9 @@ int64_t ttlda_csr_to_csc_workspace_bytes(int64_t nnz, int64_t D, int64_t V, int6
     cudaError_t e = csc_layout(nnz, nblocks * V, nullptr, w);
     if (e != cudaSuccess) return cuda_fail(e, "csr_to_csc workspace query");
     size_t need = w.total;
-    if (tile_path_applies(D, V, nblocks)) {  // whichever path runs: the larger of the two layouts
-        const TilePlan t = tile_plan(D, V);
-        if (t.total > need) need = t.total;
+    if (nblocks == 1) {  // whichever path runs (slice walk / pair sort): the larger of the two layouts
+        const WalkPlan t = walk_plan(D, V, nnz);
+        if (t.ok && t.total > need) need = t.total;
     }
     return (int64_t)need;
 }
@@ -502,8 +655,8 @@ static int csr_to_csc_impl(const int64_t* rowptr, const int32_t* colidx, const i
                            int64_t* colptr, int32_t* docidx, int32_t* ccounts, uint32_t* csr2csc, void* workspace,
                            int64_t workspace_bytes, cudaStream_t s)
 {
-    if (tile_path_applies(D, V, nblocks))
-        return csr_to_csc_tiles(rowptr, colidx, counts, D, V, nnz, doc_base, pos_base, colptr, docidx, ccounts, csr2csc,
+    if (walk_path_applies(D, V, nnz, nblocks))
+        return csr_to_csc_walk(rowptr, colidx, counts, D, V, nnz, doc_base, pos_base, colptr, docidx, ccounts, csr2csc,
                                 workspace, workspace_bytes, s);
     const int64_t VV = nblocks * V;
     CscWs w;
