@@ -629,14 +629,15 @@ def _random_rows(seed, D, V, lo, hi, empty_every=0):
 
 
 @pytest.mark.parametrize("case", ["ragged", "three_blocks", "tiny", "one_cta_per_sm", "long_documents", "many_slices",
-                                  "long_slices", "vocabulary_too_large"])
+                                  "long_slices", "very_long_slices", "longer_than_a_stage", "vocabulary_too_large"])
 def test_slice_walk_mirror_equals_sorted_mirror(monkeypatch, dev, case):
     """The default mirror — the hand-written counting sort of csrc/corpus.cu (per-slice in-order walk with 16-bit
-    shared-memory counters, scan over slices, placement) — builds the same colptr / docidx / ccounts / csr2csc, bit for
-    bit, as the generic CUB pair sort (TTLDA_CSC_WALK=0) and as a stable NumPy argsort: ragged and empty documents,
-    several document blocks, a vocabulary that leaves one CTA per SM (V > 56k), documents longer than one walk step
-    (> 512 entries), slices of more than one 512-document offsets chunk, and a vocabulary beyond the counter table
-    (V > 114 688: both settings run the generic path)."""
+    shared-memory counters fed by a cp.async stage, scan over slices, placement) — builds the same colptr / docidx /
+    ccounts / csr2csc, bit for bit, as the generic CUB pair sort (TTLDA_CSC_WALK=0) and as a stable NumPy argsort: ragged
+    and empty documents, several document blocks, a vocabulary that leaves one CTA per SM, documents longer than one walk
+    step (> 256 entries) and longer than a whole stage buffer, slices of more than one 256-document offsets chunk, many
+    small slices (generic placement), and a vocabulary beyond the counter table (V > 112 000: both settings run the
+    generic path)."""
     from tuotuo_b200.corpus import DeviceCorpus
     from tuotuo_b200.synth import numpy_corpus
 
@@ -659,8 +660,13 @@ def test_slice_walk_mirror_equals_sorted_mirror(monkeypatch, dev, case):
     elif case == "many_slices":  # 296 slices of 68 documents; V = 50k as at cfg3
         D, V = 20_000, 50_000
         rp, ci, ct = _random_rows(7, D, V, 0, 12, empty_every=5)
-    elif case == "long_slices":  # 541 documents per slice: more than one 512-document offsets chunk
-        D, V = 160_000, 200
+    elif case == "longer_than_a_stage":  # V = 100k leaves ~3 500-entry stage buffers: longer documents go straight from global
+        D, V = 40, 100_000
+        rp, ci, ct = _random_rows(10, D, V, 0, 6000, empty_every=6)
+    elif case in ("long_slices", "very_long_slices"):
+        # 541 documents per slice: more than one 256-document offsets chunk in the walk; 2 365 per slice: more than one
+        # 2 048-document chunk in the placement
+        D, V = (160_000 if case == "long_slices" else 700_000), 200
         rs = np.random.RandomState(9)
         n = rs.randint(0, 4, size=D)
         start, stride = rs.randint(0, V, size=D), rs.randint(1, 50, size=D)

@@ -223,8 +223,8 @@ static int grid_1d(int64_t n)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Mirror of ONE document block by a hand-written, comparison-free, atomic-order-free counting sort: the "slice walk".
-// (Default for blocks whose vocabulary fits the shared-memory counter table, V <= ~115 000; TTLDA_CSC_WALK=0 or a larger
+// Mirror of ONE document block by a hand-written, comparison-free counting sort: the "slice walk".
+// (Default for blocks whose vocabulary fits the shared-memory counter table, V <= ~110 000; TTLDA_CSC_WALK=0 or a larger
 // vocabulary selects the generic CUB pair sort above.)
 //
 // A CSR block is already sorted by (document, word); its mirror is the same entries sorted by (word, document) — a
@@ -236,25 +236,32 @@ static int grid_1d(int64_t n)
 //            V = 102 660) and visits its documents IN ORDER, one barrier per document: every entry takes its word's counter
 //            value as its rank inside the slice (rank[p], uint16) and increments it.  A document holds a word at most once,
 //            so inside a document no two threads meet on a counter and the ranks do not depend on thread order:
-//            deterministic.  (The increment is a shared-memory atomicAdd on the 32-bit word that holds two counters — so a
-//            malformed row with a repeated word still gets distinct, in-range ranks.)  The entries of the next kPF
-//            documents are already in registers when their turn comes.  At the end the counter table IS the slice's word
+//            deterministic.  The entries reach the walk through a double-buffered shared-memory stage filled by cp.async a
+//            group of documents ahead (a per-thread register queue of loads was tried first: with more loads in flight than
+//            the six scoreboards a thread has, waiting for the oldest waits for the youngest, and every step paid a full
+//            memory latency — 152 us per block instead of ~25).  At the end the counter table IS the slice's word
 //            histogram: hist[slice][w].
-//   2 scan   per word, the exclusive prefix of hist over the slices -> off[slice][w]; the totals -> colptr (one CTA).
-//   3 place  one warp per document: q = colptr[w] + off[slice(d)][w] + rank[p];  docidx[q] = d, (ccounts[q] = counts[p],)
-//            csr2csc[p] = q — csr2csc is one coalesced stream in CSR order.
+//   2 scan   per word, the exclusive prefix of hist over the slices -> off[slice][w], the totals, and (a second small kernel,
+//            one scan over the per-CTA sums) colptr.
+//   3 place  q = colptr[w] + off[slice(d)][w] + rank[p];  docidx[q] = d, (ccounts[q] = counts[p],) csr2csc[p] = q — one CTA
+//            per slice stages the slice's bases colptr + off in shared memory with coalesced loads and then runs flat over
+//            the slice's entries (document of an entry by binary search in the staged row offsets); csr2csc is one coalesced
+//            stream in CSR order.
 // Against the generic path (key packing, histogram, two 8-bit onesweep passes over (key, value) pairs, a dependent random
-// gather of doc ids through the sorted permutation: ~0.68 ms per 12.7M-entry block at cfg3) there is no pair sort, no
-// 20-bytes-per-entry scratch (2 bytes per entry + 6 bytes per (slice, word)), and the only serial part — the walk — is
-// ~200 barrier-separated steps per CTA.
+// gather of doc ids through the sorted permutation) there is no pair sort and no 20-bytes-per-entry scratch (2 bytes per
+// entry + 6 bytes per (slice, word)).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int kWalkThreads = 512;  // entries of one document handled per step (longer documents loop)
-constexpr int kWalkPF = 8;         // documents whose entries are prefetched into registers ahead of the walk
+constexpr int kWalkThreads = 256;      // entries of one document handled per step (longer documents loop)
+constexpr int kWalkDocs = 256;         // documents per chunk of staged row offsets
 constexpr int kWalkSmemSM = 227 * 1024;
+constexpr int kWalkMinStage = 2048;    // entries per stage buffer (2 buffers): at least
+constexpr int kWalkMaxStage = 8192;    //                                        at most
+constexpr int kPlaceThreads = 1024;
 
 struct WalkPlan {
     bool ok;
-    int64_t vp, dps, slices;
+    int64_t vp, dps, slices, parts, partw;
+    int stage_cap;  // entries per stage buffer
     size_t smem, rank_b, hist_b, off_b, total_b, total;
 };
 
@@ -262,24 +269,38 @@ static WalkPlan walk_plan(int64_t D, int64_t V, int64_t nnz)
 {
     WalkPlan w{};
     w.vp = (V + 7) / 8 * 8;  // counters are cleared / flushed as 16-byte vectors of eight
-    w.smem = (size_t)w.vp * 2;
-    // two CTAs per SM when two tables (+ 2 KB of static shared memory and the per-CTA reserve each) fit
-    const int per_sm = (2 * (w.smem + 3 * 1024) <= (size_t)kWalkSmemSM) ? 2 : 1;
-    const int64_t target = (int64_t)kSMs * per_sm;
+    // One walk CTA per slice holds the whole vocabulary's counters when they fit next to the stage buffers (V <= ~105 000);
+    // larger vocabularies are cut into `parts` word ranges, one CTA per (slice, range): every CTA of a slice sees all the
+    // slice's entries and counts those of its range.  (Ranges were also tried as a way to put four small CTAs on an SM
+    // at V = 50k: the walk got 2x SLOWER — it is bound by the instructions of a step, not by their latency, and every
+    // range repeats the steps.)
+    const size_t budget1 = (size_t)kWalkSmemSM - 4 * 1024;  // one CTA per SM: dynamic shared memory available
+    const size_t stage_min = (size_t)kWalkMinStage * 8;
+    w.parts = ((size_t)w.vp * 2 + (budget1 - stage_min) - 1) / (budget1 - stage_min);
+    if (w.parts < 1) w.parts = 1;
+    w.partw = ((w.vp + w.parts - 1) / w.parts + 7) / 8 * 8;
+    const size_t table = (size_t)w.partw * 2;
+    // two CTAs per SM when two tables + two minimal stage pairs (+ static shared memory and the per-CTA reserve) fit
+    const int64_t per = (w.parts == 1 && 2 * (table + stage_min + 4 * 1024) <= (size_t)kWalkSmemSM) ? 2 : 1;
+    const size_t budget = (size_t)kWalkSmemSM / per - 4 * 1024;
+    size_t stage = (budget - table) / 8;  // entries per buffer (two buffers of 4-byte entries)
+    if (stage > (size_t)kWalkMaxStage) stage = kWalkMaxStage;
+    w.stage_cap = (int)(stage / 4 * 4);
+    w.smem = table + (size_t)w.stage_cap * 8;
+    const int64_t target = (int64_t)kSMs * per;  // slices: one wave of walk CTAs (parts waves for a cut vocabulary)
     w.dps = (D + target - 1) / target;
     if (w.dps < 16) w.dps = 16;
     w.slices = D > 0 ? (D + w.dps - 1) / w.dps : 1;
-    w.ok = V >= 1 && w.smem + 3 * 1024 <= (size_t)kWalkSmemSM && w.dps <= 65535 && nnz < ((int64_t)1 << 31) &&
-           target * w.vp < ((int64_t)1 << 32);
+    w.ok = V >= 1 && w.parts <= 64 && w.dps <= 65535 && nnz < ((int64_t)1 << 31) && target * w.vp < ((int64_t)1 << 32);
     // buffer sizes from a bound on the slice count that is monotone in D (the workspace is sized for the largest block, a
     // call may bring a smaller one: slices <= target and slices <= ceil(D / 16) always hold)
     int64_t cap = (D + 15) / 16;
     if (cap > target) cap = target;
     if (cap < 1) cap = 1;
-    w.rank_b = align256((size_t)(nnz > 0 ? nnz : 1) * 2);
+    w.rank_b = align256((size_t)(nnz > 0 ? nnz : 1) * 4);
     w.hist_b = align256((size_t)cap * w.vp * 2);
     w.off_b = align256((size_t)cap * w.vp * 4);
-    w.total_b = align256((size_t)w.vp * 4 + 16);  // + the redo flag
+    w.total_b = align256((size_t)w.vp * 4 + 16) + align256((size_t)(w.vp / 512 + 2) * 8);  // totals, redo flag, CTA sums
     w.total = w.rank_b + w.hist_b + w.off_b + w.total_b;
     return w;
 }
@@ -292,178 +313,275 @@ static bool walk_path_applies(int64_t D, int64_t V, int64_t nnz, int64_t nblocks
     return walk_plan(D, V, nnz).ok;
 }
 
+__device__ __forceinline__ void walk_cp_async4(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void walk_cp_async16(uint32_t dst, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void walk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void walk_cp_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // 1: the walk.  rank[p] = documents of the slice before p's that contain p's word;  hist[slice][*] = the slice's word counts.
 // Also fills docidx[.] of the slice's entry range with a valid document id, so that whatever a malformed corpus makes of
 // the placement (3), no slot of the mirror is left holding garbage that a gather would follow.
 //
-// ATOMIC = false (the fast form): the counter update is a plain 16-bit LDS + STS — a shared-memory atomic costs ~2 cycles
-// per LANE on this part (64 per warp instruction) and made the walk 3x slower than the rest of the sort.  That is only
-// right when no document repeats a word, which holds for every row the reference can produce (np.nonzero) and is what
-// Document.from_csr checks; the kernel checks it again on the fly (each entry against its predecessor: strictly ascending)
-// and raises *redo if a row fails.  ATOMIC = true is the same walk with atomicAdd on the 32-bit word that holds two
-// counters: launched right behind the fast form, it returns at once unless *redo is set, and then recomputes the block's
-// ranks and histograms correctly for ANY row order / repetition (distinct, in-range ranks).
+// ATOMIC = false (the fast form): the counter update is a plain 16-bit LDS + STS.  That is only right when no document
+// repeats a word, which holds for every row the reference can produce (np.nonzero) and is what Document.from_csr checks; the
+// kernel checks it again on the fly (each entry against its predecessor: strictly ascending) and raises *redo if a row
+// fails.  ATOMIC = true is the same walk with atomicAdd on the 32-bit word that holds two counters: launched right behind
+// the fast form, it returns at once unless *redo is set, and then recomputes the block's ranks and histograms correctly for
+// ANY row order / repetition (distinct, in-range ranks).
 template <bool ATOMIC>
 __global__ void __launch_bounds__(kWalkThreads) csc_walk_kernel(const int64_t* __restrict__ rowptr,
                                                                 const int32_t* __restrict__ colidx, int64_t D, int64_t V,
-                                                                int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base,
-                                                                uint16_t* __restrict__ rank, uint32_t* __restrict__ hist32,
+                                                                int64_t vp, int64_t partw, int64_t dps, int cap,
+                                                                int64_t doc_base, int64_t pos_base,
+                                                                uint32_t* __restrict__ rank, uint32_t* __restrict__ hist32,
                                                                 int32_t* __restrict__ docidx, int32_t* __restrict__ redo)
 {
-    extern __shared__ __align__(16) uint32_t walk_tab[];  // vp / 2 words, two 16-bit counters each
-    __shared__ int s_off[kWalkThreads + 1];               // entry offsets of up to kWalkThreads documents
+    extern __shared__ __align__(16) uint32_t walk_tab[];  // partw / 2 words (two 16-bit counters each), 2 stages of `cap`
+    __shared__ int s_off[kWalkDocs + 1];                  // entry offsets of up to kWalkDocs documents
     if (ATOMIC && *redo == 0) return;
     const int t = threadIdx.x;
-    const int half = (int)(vp >> 1);
+    const int wlo = (int)(blockIdx.y * partw);                                   // this CTA's word range [wlo, wlo + wn)
+    const int wn = (int)((wlo + partw <= vp) ? partw : (vp > wlo ? vp - wlo : 0));
+    const int half = wn >> 1;
+    const bool first_part = blockIdx.y == 0;
+    int32_t* stage = reinterpret_cast<int32_t*>(walk_tab + (partw >> 1));
+    const uint32_t stage_u32 = (uint32_t)__cvta_generic_to_shared(stage);
     const int64_t d_lo = (int64_t)blockIdx.x * dps;
     const int64_t d_hi = (d_lo + dps < D) ? d_lo + dps : D;
     for (int i = t * 4; i < half; i += kWalkThreads * 4) *reinterpret_cast<uint4*>(walk_tab + i) = make_uint4(0u, 0u, 0u, 0u);
     uint16_t* tab16 = reinterpret_cast<uint16_t*>(walk_tab);
     bool unordered = false;
 
-    auto place = [&](int w, int64_t p) {
-        if (!ATOMIC) docidx[p] = (int32_t)doc_base;
-        unsigned r = 0;
-        if ((unsigned)w < (unsigned)V) {
+    // jl: the document's index inside the slice; what is left for the placement is (jl << 16) | rank
+    auto place = [&](int w, int64_t p, unsigned jl) {
+        if (!ATOMIC && first_part) docidx[p] = (int32_t)doc_base;
+        const unsigned x = (unsigned)(w - wlo);
+        if (x < (unsigned)wn) {  // a word of this CTA's range (ids outside [0, vp) are nobody's: the placement skips them)
+            unsigned r;
             if (ATOMIC) {
-                const unsigned sh = (unsigned)(w & 1) << 4;
-                r = atomicAdd(walk_tab + (w >> 1), 1u << sh) >> sh;
+                const unsigned sh = (x & 1u) << 4;
+                r = (atomicAdd(walk_tab + (x >> 1), 1u << sh) >> sh) & 0xffffu;
             } else {
-                r = tab16[w];
-                tab16[w] = (uint16_t)(r + 1);
+                r = tab16[x];
+                tab16[x] = (uint16_t)(r + 1);
             }
+            rank[p] = (jl << 16) | r;
         }
-        rank[p] = (uint16_t)r;
     };
 
-    for (int64_t c0 = d_lo; c0 < d_hi; c0 += kWalkThreads) {
-        const int n = (int)((d_hi - c0 < kWalkThreads) ? d_hi - c0 : kWalkThreads);
-        __syncthreads();  // the table is cleared / the previous chunk's offsets are no longer read
+    for (int64_t c0 = d_lo; c0 < d_hi; c0 += kWalkDocs) {
+        const int n = (int)((d_hi - c0 < kWalkDocs) ? d_hi - c0 : kWalkDocs);
+        __syncthreads();  // the table is cleared / the previous chunk's offsets and stages are no longer read
         const int64_t base = rowptr[c0] - pos_base;
         for (int i = t; i <= n; i += kWalkThreads) s_off[i] = (int)(rowptr[c0 + i] - pos_base - base);
         __syncthreads();
         const int32_t* ci = colidx + base;
-        int wq[kWalkPF], pq[kWalkPF];  // this thread's entry of the next kWalkPF documents, and the entry before it
-#pragma unroll
-        for (int u = 0; u < kWalkPF; ++u) {
-            wq[u] = -1;
-            pq[u] = -1;
-            if (u < n && s_off[u] + t < s_off[u + 1]) {
-                wq[u] = ci[s_off[u] + t];
-                if (!ATOMIC && t > 0) pq[u] = ci[s_off[u] + t - 1];
+        // the documents [j0, j1) whose entries fit one stage buffer; j1 == j0: document j0 alone is longer than a buffer
+        // (a stage buffer also holds up to 3 entries in front of the group's first one: the copies are 16 bytes wide and
+        // start at the 16-byte boundary at or below it — 4-byte cp.async costs the LSU as much per instruction and made
+        // the fill, not the walk, the bound)
+        auto sub_end = [&](int j0) {
+            const int lim = s_off[j0] + cap - 4;
+            int lo = j0, hi = n + 1;  // largest j in [j0, n] with s_off[j] <= lim
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s_off[mid] <= lim) lo = mid; else hi = mid;
             }
-        }
-        for (int j0 = 0; j0 < n; j0 += kWalkPF) {
-#pragma unroll
-            for (int u = 0; u < kWalkPF; ++u) {
-                const int j = j0 + u;
-                if (j < n) {  // CTA-uniform
-                    const int b = s_off[j], e = s_off[j + 1];
-                    const int w = wq[u], wp = pq[u];
-                    const bool mine = b + t < e;
-                    wq[u] = -1;
-                    pq[u] = -1;
-                    if (j + kWalkPF < n && s_off[j + kWalkPF] + t < s_off[j + kWalkPF + 1]) {
-                        wq[u] = ci[s_off[j + kWalkPF] + t];
-                        if (!ATOMIC && t > 0) pq[u] = ci[s_off[j + kWalkPF] + t - 1];
+            return lo;
+        };
+        // returns the number of leading pad entries: entry s_off[j0] + i of the corpus sits at stage[buf][lead + i]
+        auto fill = [&](int buf, int j0, int j1) {
+            const int b = s_off[j0], cnt = s_off[j1] - b;
+            const int lead = (int)((reinterpret_cast<uintptr_t>(ci + b) & 15) >> 2);
+            const int32_t* src = ci + b - lead;  // 16-byte aligned; the pad entries belong to this block or to the array
+                                                 // in front of it (b - lead >= 0 whenever lead > 0: the base is aligned)
+            const uint32_t dst = stage_u32 + (uint32_t)buf * (uint32_t)cap * 4u;
+            const int nvec = (lead + cnt) >> 2;  // whole 16-byte vectors
+            for (int i = t; i < nvec; i += kWalkThreads) walk_cp_async16(dst + 16u * (uint32_t)i, src + 4 * i);
+            const int tail = (lead + cnt) & 3;  // the last 1..3 entries: 4-byte copies, nothing is read past the group
+            if (t < tail) walk_cp_async4(dst + 4u * (uint32_t)(4 * nvec + t), src + 4 * nvec + t);
+            return lead;
+        };
+        int j0 = 0, buf = 0, lead0 = 0, lead1 = 0;
+        int j1 = sub_end(0);
+        bool long0 = (j1 == 0);
+        if (long0) j1 = 1; else lead0 = fill(0, 0, j1);
+        walk_cp_commit();
+        while (j0 < n) {
+            int j2 = j1;
+            bool long1 = false;
+            if (j1 < n) {
+                j2 = sub_end(j1);
+                long1 = (j2 == j1);
+                if (long1) j2 = j1 + 1; else lead1 = fill(buf ^ 1, j1, j2);
+            }
+            walk_cp_commit();
+            walk_cp_wait<1>();  // this thread's copies of the current group have landed ...
+            __syncthreads();    // ... and so have everybody else's
+            if (long0) {  // one document longer than a stage buffer: straight from global memory
+                const int b = s_off[j0], e = s_off[j0 + 1];
+                const unsigned jl = (unsigned)(c0 - d_lo) + (unsigned)j0;
+                for (int i = b + t; i < e; i += kWalkThreads) {
+                    const int w = ci[i];
+                    if (i > b) unordered |= (w <= ci[i - 1]);
+                    place(w, base + i, jl);
+                }
+                __syncthreads();
+            } else {
+                // the entry a thread handles in document j + 1 is fetched from the stage while document j is being counted:
+                // between two barriers only the counter update (LDS -> STS) is left on the critical path
+                const int32_t* st = stage + (size_t)buf * cap + lead0 - s_off[j0];
+                int b = s_off[j0], e = s_off[j0 + 1];
+                int wn = -1, wpn = -1;
+                if (b + t < e) {
+                    wn = st[b + t];
+                    if (t > 0) wpn = st[b + t - 1];
+                }
+                for (int j = j0; j < j1; ++j) {
+                    const int cb = b, ce = e, w = wn, wp = wpn;
+                    if (j + 1 < j1) {
+                        b = ce;
+                        e = s_off[j + 2];
+                        wn = -1;
+                        wpn = -1;
+                        if (b + t < e) {
+                            wn = st[b + t];
+                            if (t > 0) wpn = st[b + t - 1];
+                        }
                     }
-                    if (mine) {
-                        unordered |= (w <= wp);  // wp = -1 for a document's first entry; ids are >= 0 (else flagged later)
-                        place(w, base + b + t);
+                    const unsigned jl = (unsigned)(c0 - d_lo) + (unsigned)j;
+                    if (cb + t < ce) {
+                        unordered |= (w <= wp);  // wp = -1 for a document's first entry
+                        place(w, base + cb + t, jl);
                     }
-                    for (int i = b + t + kWalkThreads; i < e; i += kWalkThreads) {  // long documents
-                        const int wl = ci[i];
-                        unordered |= (wl <= ci[i - 1]);
-                        place(wl, base + i);
+                    for (int i = cb + t + kWalkThreads; i < ce; i += kWalkThreads) {  // long documents
+                        const int wl = st[i];
+                        unordered |= (wl <= st[i - 1]);
+                        place(wl, base + i, jl);
                     }
                     __syncthreads();  // document j is counted before document j + 1 reads the counters
                 }
             }
+            j0 = j1;
+            j1 = j2;
+            long0 = long1;
+            lead0 = lead1;
+            buf ^= 1;
         }
+        walk_cp_wait<0>();
     }
     if (!ATOMIC && unordered) *redo = 1;
     __syncthreads();
-    uint32_t* out = hist32 + (size_t)blockIdx.x * half;
+    uint32_t* out = hist32 + (size_t)blockIdx.x * (size_t)(vp >> 1) + (wlo >> 1);
     for (int i = t * 4; i < half; i += kWalkThreads * 4)
         *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(walk_tab + i);
 }
 
-// 2: per word, exclusive prefix of the slice counts and the total; one thread per PAIR of words (the packed counters)
+// 2a: per word, exclusive prefix of the slice counts and the total; one thread per PAIR of words (the packed counters);
+// bsum[CTA] = the sum of the CTA's 512 totals (for 2b)
 __global__ void __launch_bounds__(256) csc_walk_scan_kernel(const uint32_t* __restrict__ hist32, int64_t slices, int64_t vp,
-                                                            uint32_t* __restrict__ off, uint32_t* __restrict__ total)
+                                                            uint32_t* __restrict__ off, uint32_t* __restrict__ total,
+                                                            int64_t* __restrict__ bsum)
 {
+    __shared__ int64_t wsum[8];
     const int64_t half = vp >> 1;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= half) return;
     uint32_t r0 = 0, r1 = 0;
-    int64_t s = 0;
-    for (; s + 8 <= slices; s += 8) {
-        uint32_t h[8];
+    if (i < half) {
+        int64_t s = 0;
+        for (; s + 16 <= slices; s += 16) {
+            uint32_t h[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) h[u] = hist32[(s + u) * half + i];
+            for (int u = 0; u < 16; ++u) h[u] = hist32[(s + u) * half + i];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            *reinterpret_cast<uint2*>(off + (s + u) * vp + 2 * i) = make_uint2(r0, r1);
-            r0 += h[u] & 0xffffu;
-            r1 += h[u] >> 16;
-        }
-    }
-    for (; s < slices; ++s) {
-        const uint32_t h = hist32[s * half + i];
-        *reinterpret_cast<uint2*>(off + s * vp + 2 * i) = make_uint2(r0, r1);
-        r0 += h & 0xffffu;
-        r1 += h >> 16;
-    }
-    *reinterpret_cast<uint2*>(total + 2 * i) = make_uint2(r0, r1);
-}
-
-// colptr[w] = pos_base + sum_{w' < w} total[w'] (never beyond the block: pos_base + nnz), colptr[V] = pos_base + nnz.
-// One CTA scans the totals 1024 at a time (coalesced loads, warp shuffles, a running carry).
-__global__ void __launch_bounds__(1024) csc_colptr_kernel(const uint32_t* __restrict__ total, int64_t V, int64_t pos_base,
-                                                          int64_t nnz, int64_t* __restrict__ colptr)
-{
-    __shared__ int64_t wsum[32];
-    __shared__ int64_t carry_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) carry_s = 0;
-    __syncthreads();
-    for (int64_t c0 = 0; c0 < V; c0 += 1024) {
-        const int64_t w = c0 + tid;
-        const int64_t v = (w < V) ? (int64_t)total[w] : 0;
-        int64_t x = v;  // inclusive scan inside the warp
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) wsum[warp] = x;
-        __syncthreads();
-        if (warp == 0) {
-            int64_t s = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int64_t y = __shfl_up_sync(0xffffffffu, s, o);
-                if (lane >= o) s += y;
+            for (int u = 0; u < 16; ++u) {
+                *reinterpret_cast<uint2*>(off + (s + u) * vp + 2 * i) = make_uint2(r0, r1);
+                r0 += h[u] & 0xffffu;
+                r1 += h[u] >> 16;
             }
-            wsum[lane] = s;  // inclusive over the warps
         }
-        __syncthreads();
-        const int64_t carry = carry_s;
-        const int64_t excl = carry + (warp ? wsum[warp - 1] : 0) + (x - v);
-        if (w < V) colptr[w] = pos_base + (excl < nnz ? excl : nnz);
-        __syncthreads();
-        if (tid == 1023) carry_s = carry + wsum[31];
-        __syncthreads();
+        for (; s < slices; ++s) {
+            const uint32_t h = hist32[s * half + i];
+            *reinterpret_cast<uint2*>(off + s * vp + 2 * i) = make_uint2(r0, r1);
+            r0 += h & 0xffffu;
+            r1 += h >> 16;
+        }
+        *reinterpret_cast<uint2*>(total + 2 * i) = make_uint2(r0, r1);
     }
-    if (tid == 0) colptr[V] = pos_base + nnz;
+    int64_t x = (int64_t)r0 + (int64_t)r1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t sum = 0;
+        for (int k = 0; k < 8; ++k) sum += wsum[k];
+        bsum[blockIdx.x] = sum;
+    }
 }
 
-// 3: placement, one warp per document
+// 2b: colptr[w] = pos_base + sum_{w' < w} total[w'] (never beyond the block: pos_base + nnz), colptr[V] = pos_base + nnz.
+// Same CTA partition as 2a: a CTA adds up the sums of the CTAs before it, then scans its own 512 totals.
+__global__ void __launch_bounds__(256) csc_colptr_kernel(const uint32_t* __restrict__ total,
+                                                         const int64_t* __restrict__ bsum, int64_t V, int64_t vp,
+                                                         int64_t pos_base, int64_t nnz, int64_t* __restrict__ colptr)
+{
+    __shared__ int64_t wsum[8];
+    __shared__ int64_t before_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int64_t before = 0;
+    for (int c = tid; c < (int)blockIdx.x; c += 256) before += bsum[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    if (lane == 0) wsum[warp] = before;
+    __syncthreads();
+    if (tid == 0) {
+        int64_t sum = 0;
+        for (int k = 0; k < 8; ++k) sum += wsum[k];
+        before_s = sum;
+    }
+    __syncthreads();
+    before = before_s;
+    const int64_t i = (int64_t)blockIdx.x * 256 + tid;  // word pair
+    uint2 tt = make_uint2(0u, 0u);
+    if (2 * i < vp) tt = *reinterpret_cast<const uint2*>(total + 2 * i);
+    const int64_t v = (int64_t)tt.x + (int64_t)tt.y;
+    int64_t x = v;  // inclusive scan over the CTA's pairs
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    __syncthreads();
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    int64_t wbefore = 0;
+    for (int k = 0; k < warp; ++k) wbefore += wsum[k];
+    const int64_t excl = before + wbefore + (x - v);
+    if (2 * i < V) colptr[2 * i] = pos_base + (excl < nnz ? excl : nnz);
+    if (2 * i + 1 < V) {
+        const int64_t e1 = excl + (int64_t)tt.x;
+        colptr[2 * i + 1] = pos_base + (e1 < nnz ? e1 : nnz);
+    }
+    if (blockIdx.x == gridDim.x - 1 && tid == 0) colptr[V] = pos_base + nnz;
+}
+
+// 3 (generic form, vocabularies whose 32-bit bases do not fit shared memory): one warp per document
 __global__ void __launch_bounds__(256) csc_walk_place_kernel(const int64_t* __restrict__ rowptr,
                                                              const int32_t* __restrict__ colidx,
                                                              const int32_t* __restrict__ counts, int64_t D, int64_t V,
                                                              int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base,
-                                                             int64_t nnz, const uint16_t* __restrict__ rank,
+                                                             int64_t nnz, const uint32_t* __restrict__ rank,
                                                              const uint32_t* __restrict__ off,
                                                              const int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
                                                              int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
@@ -478,7 +596,7 @@ __global__ void __launch_bounds__(256) csc_walk_place_kernel(const int64_t* __re
             const int w = colidx[p];
             int64_t q = p;  // a word id outside [0, V) (malformed, and not sanitised by the caller): stay in bounds
             if ((unsigned)w < (unsigned)V) {
-                q = (colptr[w] - pos_base) + (int64_t)offs[w] + (int64_t)rank[p];
+                q = (colptr[w] - pos_base) + (int64_t)offs[w] + (int64_t)(rank[p] & 0xffffu);
                 if (q >= nnz) q = nnz - 1;  // only a corpus that overflows a 16-bit counter (> 65 535 repeats) gets here
                 docidx[q] = (int32_t)(doc_base + d);
                 if (ccounts) ccounts[q] = counts[p];
@@ -488,33 +606,79 @@ __global__ void __launch_bounds__(256) csc_walk_place_kernel(const int64_t* __re
     }
 }
 
-// 3, when a 32-bit entry per word fits shared memory (V <= ~57 000): one CTA per SLICE first stages the slice's placement
+// 3, when a 32-bit entry per word fits shared memory (V <= ~55 000): one CTA per SLICE first stages the slice's placement
 // bases colptr[w] + off[slice][w] with coalesced loads (the generic form above fetches them with two dependent random
-// 4/8-byte reads per entry: a 32-byte sector each), then places its documents' entries from shared memory.
-constexpr int kPlaceThreads = 1024;
+// 4/8-byte reads per entry: a 32-byte sector each), then runs FLAT over the slice's entries — the walk left the document's
+// index inside the slice next to the rank, so an entry needs nothing but its own (word, rank | doc) pair.  Four entries per
+// thread are processed while the next four are in flight.
 __global__ void __launch_bounds__(kPlaceThreads) csc_walk_place_slice_kernel(
     const int64_t* __restrict__ rowptr, const int32_t* __restrict__ colidx, const int32_t* __restrict__ counts, int64_t D,
-    int64_t V, int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base, int64_t nnz, const uint16_t* __restrict__ rank,
+    int64_t V, int64_t vp, int64_t dps, int64_t doc_base, int64_t pos_base, int64_t nnz, const uint32_t* __restrict__ rank,
     const uint32_t* __restrict__ off, const int64_t* __restrict__ colptr, int32_t* __restrict__ docidx,
     int32_t* __restrict__ ccounts, uint32_t* __restrict__ csr2csc)
 {
     extern __shared__ __align__(16) uint32_t place_base[];  // vp words
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const uint32_t* offs = off + (size_t)blockIdx.x * vp;
-    for (int64_t w = t; w < V; w += kPlaceThreads) place_base[w] = (uint32_t)(colptr[w] - pos_base) + offs[w];
-    __syncthreads();
+    const int t = threadIdx.x;
     const int64_t d_lo = (int64_t)blockIdx.x * dps;
     const int64_t d_hi = (d_lo + dps < D) ? d_lo + dps : D;
-    for (int64_t d = d_lo + warp; d < d_hi; d += kPlaceThreads / 32) {
-        const int64_t b = rowptr[d] - pos_base, e = rowptr[d + 1] - pos_base;
-        for (int64_t p = b + lane; p < e; p += 32) {
-            const int w = colidx[p];
+    const int p0 = (int)(rowptr[d_lo] - pos_base), p1 = (int)(rowptr[d_hi] - pos_base);
+    constexpr int U = 4, STEP = U * kPlaceThreads;
+    int w[U], rk[U], c[U];
+    auto fetch = [&](int pb) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * kPlaceThreads;
+            w[u] = -1;
+            rk[u] = 0;
+            c[u] = 0;
+            if (p < p1) {
+                w[u] = colidx[p];
+                rk[u] = (int)rank[p];
+                if (ccounts) c[u] = counts[p];
+            }
+        }
+    };
+    fetch(p0 + t);  // in flight while the bases are staged
+    const uint32_t* offs = off + (size_t)blockIdx.x * vp;
+    for (int64_t w0 = t; w0 < V; w0 += 8 * kPlaceThreads) {  // eight independent (colptr, off) pairs in flight per thread
+        int64_t cp[8];
+        uint32_t of[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t ww = w0 + u * kPlaceThreads;
+            cp[u] = 0;
+            of[u] = 0;
+            if (ww < V) {
+                cp[u] = colptr[ww];
+                of[u] = offs[ww];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t ww = w0 + u * kPlaceThreads;
+            if (ww < V) place_base[ww] = (uint32_t)(cp[u] - pos_base) + of[u];
+        }
+    }
+    __syncthreads();
+    for (int pb = p0 + t; pb < p1; pb += STEP) {
+        int cw[U], crk[U], cc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cw[u] = w[u];
+            crk[u] = rk[u];
+            cc[u] = c[u];
+        }
+        fetch(pb + STEP);  // the next four entries: in flight while these four are placed
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int p = pb + u * kPlaceThreads;
+            if (p >= p1) continue;
             int64_t q = p;  // a word id outside [0, V): stay in bounds (see the generic form)
-            if ((unsigned)w < (unsigned)V) {
-                q = (int64_t)place_base[w] + (int64_t)rank[p];
+            if ((unsigned)cw[u] < (unsigned)V) {
+                q = (int64_t)place_base[cw[u]] + (int64_t)((unsigned)crk[u] & 0xffffu);
                 if (q >= nnz) q = nnz - 1;
-                docidx[q] = (int32_t)(doc_base + d);
-                if (ccounts) ccounts[q] = counts[p];
+                docidx[q] = (int32_t)(doc_base + d_lo + (int64_t)((unsigned)crk[u] >> 16));
+                if (ccounts) ccounts[q] = cc[u];
             }
             if (csr2csc) csr2csc[p] = (uint32_t)(pos_base + q);
         }
@@ -531,49 +695,48 @@ static int csr_to_csc_walk(const int64_t* rowptr, const int32_t* colidx, const i
         return TTLDA_EWORKSPACE;
     }
     char* base = (char*)workspace;
-    uint16_t* rank = (uint16_t*)base;
+    uint32_t* rank = (uint32_t*)base;  // (document index inside the slice << 16) | rank inside the slice, per entry
     uint32_t* hist32 = (uint32_t*)(base + w.rank_b);
     uint32_t* off = (uint32_t*)(base + w.rank_b + w.hist_b);
     uint32_t* total = (uint32_t*)(base + w.rank_b + w.hist_b + w.off_b);
     int32_t* redo = (int32_t*)(total + w.vp);  // "a row repeats or misorders words: redo the walk with atomics"
+    int64_t* bsum = (int64_t*)((char*)total + align256((size_t)w.vp * 4 + 16));
+    const unsigned scan_grid = (unsigned)((w.vp / 2 + 255) / 256);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(csc_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kWalkSmemSM - 3 * 1024);
+                                             kWalkSmemSM - 4 * 1024);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(csc_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kWalkSmemSM - 3 * 1024);
+                                     kWalkSmemSM - 4 * 1024);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(csc_walk_place_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kWalkSmemSM - 12 * 1024);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_walk)");
         configured = true;
     }
     if (D > 0 && nnz > 0) {
         cudaError_t e = cudaMemsetAsync(redo, 0, sizeof(int32_t), s);
         if (e != cudaSuccess) return cuda_fail(e, "memset redo flag");
-        csc_walk_kernel<false><<<(unsigned)w.slices, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.dps, doc_base,
-                                                                                  pos_base, rank, hist32, docidx, redo);
+        const dim3 wgrid((unsigned)w.slices, (unsigned)w.parts);
+        csc_walk_kernel<false><<<wgrid, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.partw, w.dps, w.stage_cap,
+                                                                  doc_base, pos_base, rank, hist32, docidx, redo);
         TTLDA_LAUNCH_CHECK("csc_walk");
-        csc_walk_kernel<true><<<(unsigned)w.slices, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.dps, doc_base,
-                                                                                 pos_base, rank, hist32, docidx, redo);
+        csc_walk_kernel<true><<<wgrid, kWalkThreads, w.smem, s>>>(rowptr, colidx, D, V, w.vp, w.partw, w.dps, w.stage_cap,
+                                                                 doc_base, pos_base, rank, hist32, docidx, redo);
         TTLDA_LAUNCH_CHECK("csc_walk (atomic redo)");
-        csc_walk_scan_kernel<<<(unsigned)((w.vp / 2 + 255) / 256), 256, 0, s>>>(hist32, w.slices, w.vp, off, total);
+        csc_walk_scan_kernel<<<scan_grid, 256, 0, s>>>(hist32, w.slices, w.vp, off, total, bsum);
         TTLDA_LAUNCH_CHECK("csc_walk_scan");
     } else {
-        cudaError_t e = cudaMemsetAsync(total, 0, (size_t)w.vp * 4, s);
+        cudaError_t e = cudaMemsetAsync(total, 0, (size_t)((char*)(bsum + scan_grid) - (char*)total), s);
         if (e != cudaSuccess) return cuda_fail(e, "memset totals");
     }
-    csc_colptr_kernel<<<1, 1024, 0, s>>>(total, V, pos_base, nnz, colptr);
+    csc_colptr_kernel<<<scan_grid, 256, 0, s>>>(total, bsum, V, w.vp, pos_base, nnz, colptr);
     TTLDA_LAUNCH_CHECK("csc_colptr");
     if (D > 0 && nnz > 0) {
         const size_t place_smem = (size_t)w.vp * 4;
         // (staging V bases per slice only pays when the slice has entries to place with them)
-        if (place_smem + 3 * 1024 <= (size_t)kWalkSmemSM && nnz / w.slices >= w.vp / 4) {
-            static bool place_configured = false;
-            if (!place_configured) {
-                cudaError_t e = cudaFuncSetAttribute(csc_walk_place_slice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                     kWalkSmemSM - 3 * 1024);
-                if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(csc_walk_place_slice)");
-                place_configured = true;
-            }
+        if (place_smem + 12 * 1024 <= (size_t)kWalkSmemSM && nnz / w.slices >= w.vp / 4) {
             csc_walk_place_slice_kernel<<<(unsigned)w.slices, kPlaceThreads, place_smem, s>>>(
                 rowptr, colidx, counts, D, V, w.vp, w.dps, doc_base, pos_base, nnz, rank, off, colptr, docidx, ccounts,
                 csr2csc);

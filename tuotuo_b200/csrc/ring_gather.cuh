@@ -28,12 +28,32 @@ inline bool ring_gather_enabled()
 
 // sub-batches per warp in the ring (NSTAGE - 1 in flight while one is consumed), by shape: what 16 / 12 / 8 resident warps
 // (128 / 168 / 255 registers) can hold in ~200 KB of shared memory — a stage is 32/G rows of up to 2 G E doubles
-__host__ __device__ constexpr int ring_stages(int G, int E) { return (G == 8 && E <= 7) ? 4 : 3; }
-__host__ __device__ constexpr int ring_min_ctas(int E) { return E <= 7 ? 4 : (E <= 12 ? 3 : 2); }  // of 4 warps each
+// (the TTLDA_RING_* macros exist for same-box A/B builds: tools/build_variant.sh)
+#ifndef TTLDA_RING_STAGES_SMALL
+#define TTLDA_RING_STAGES_SMALL 4
+#endif
+#ifndef TTLDA_RING_STAGES_LARGE
+#define TTLDA_RING_STAGES_LARGE 3
+#endif
+#ifndef TTLDA_RING_CTAS_SMALL
+#define TTLDA_RING_CTAS_SMALL 4
+#endif
+__host__ __device__ constexpr int ring_stages(int G, int E)
+{
+    return (G == 8 && E <= 7) ? TTLDA_RING_STAGES_SMALL : TTLDA_RING_STAGES_LARGE;
+}
+__host__ __device__ constexpr int ring_min_ctas(int E)  // CTAs of 4 warps each
+{
+    return E <= 7 ? TTLDA_RING_CTAS_SMALL : (E <= 12 ? 3 : 2);
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src)
 {
+#ifdef TTLDA_RING_CA
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#else
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
