@@ -1069,39 +1069,6 @@ def test_edge_cases_vs_oracle(K, V, rows, fixed_point):
     assert relerr(m._gamma_, o.gamma) < tol and relerr(m._lambda_, o.lam) < tol
 
 
-@pytest.mark.parametrize("K", [66, 100, 128, 200, 500, 1000])
-def test_cp_async_ring_estep_is_exact(monkeypatch, K):
-    """TTLDA_RING=1: the E-step / ELBO pass with exp(E[log beta]) rows staged through the per-lane cp.async ring
-    (csrc/ring_gather.cuh) — lane groups of 8, 16 and 32, 3- and 4-stage rings; documents shorter than the look-ahead, ragged and empty
-    documents; same answers as the oracle, and bit-identical to the register-staged walk (same arithmetic order)."""
-    from tuotuo.document import Document
-    from tuotuo.lda_model import LDASmoothed
-    from tuotuo_b200.synth import numpy_corpus
-
-    V = 900
-    rp, ci, ct = numpy_corpus(710 + K, 300, V, 25, 70, ragged=True)
-    # a few very short documents (1..5 distinct words: fewer sub-batches than ring stages) and an empty one
-    keep = np.ones(len(ci), bool)
-    for d, n in ((3, 1), (4, 2), (5, 5), (6, 0), (7, 9)):
-        keep[rp[d] + n:rp[d + 1]] = False
-    lens = np.add.reduceat(keep, rp[:-1]) * (np.diff(rp) > 0)
-    rp2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
-    ci, ct = ci[keep], ct[keep]
-    o = OracleLDA(K, engine="c")
-    po = o.fit(CSRCorpus(rp2, ci, ct, V), em_num_step=3)
-    base = LDASmoothed(K, verbose=False)
-    pb = base.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
-    monkeypatch.setenv("TTLDA_RING", "1")
-    m = LDASmoothed(K, verbose=False)
-    pg = m.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
-    assert relerr(pg, po) < TOL_PERP and relerr(m._gamma_, o.gamma) < TOL_STATE and relerr(m._lambda_, o.lam) < TOL_STATE
-    assert np.array_equal(m._gamma_, base._gamma_) and np.array_equal(m._lambda_, base._lambda_) and list(pg) == list(pb)
-    monkeypatch.setenv("TTLDA_FUSED_REFRESH", "1")  # MODE 1 kernel as well
-    m2 = LDASmoothed(K, verbose=False)
-    p2 = m2.fit(Document.from_csr(rp2, ci, ct, V), em_num_step=3, return_perplexities=True)
-    assert relerr(p2, po) < TOL_PERP and relerr(m2._gamma_, o.gamma) < TOL_STATE
-
-
 @pytest.mark.parametrize("K", [70, 100, 128])
 def test_tma_gather4_variants_are_exact(monkeypatch, K):
     """TTLDA_TMA=1: K-vector rows fed by the TMA engine (cp.async.bulk.tensor ... tile::gather4 + mbarrier pipeline)

@@ -16,7 +16,6 @@
 // partials are transposed through shared memory to a 32-lane layout (k = lane + 32m), then
 // gamma_k = alpha_k + eT_k * acc_k, AS-103 psi, exp, lgamma => new exp(E[log theta_d]) and the theta-prior term.
 // Bound: gather of 8K bytes per nonzero (L2 when the 8*K*V-byte table fits, else HBM).
-#include "ring_gather.cuh"
 #include "tma_gather.cuh"
 
 namespace ttlda {
@@ -43,7 +42,14 @@ struct EStepParams {
     double* records;
 };
 
-constexpr int kDocThreads = 128;  // 4 warps per CTA
+// (TTLDA_DOC_THREADS / TTLDA_DOC_MINB: same-box A/B builds of the CTA shape, tools/build_variant.sh)
+#ifndef TTLDA_DOC_THREADS
+#define TTLDA_DOC_THREADS 128
+#endif
+#ifndef TTLDA_DOC_MINB
+#define TTLDA_DOC_MINB 3
+#endif
+constexpr int kDocThreads = TTLDA_DOC_THREADS;  // 4 warps per CTA
 
 // Per-document epilogue shared by the LDG- and TMA-fed kernels: group partials -> 32-lane layout through shared
 // memory, gamma_d = alpha + eT_d * acc (lda_model.py:248), the reference's loop statistics, and (MODE 1) the theta
@@ -123,7 +129,11 @@ __device__ __forceinline__ void doc_epilogue(const EStepParams& P, int64_t d, co
 // epilogue;  2: E-step writing gamma only (the refresh is then run as the separate, fully parallel theta_refresh pass:
 // the epilogue's digamma/log-gamma/exp chains otherwise sit on the critical path of a warp that has nothing else to do)
 template <int G, int E, bool PREFETCH, int MODE>
-__global__ void __launch_bounds__(kDocThreads, (E <= 8 ? 3 : 1)) doc_pass_kernel(const EStepParams P)
+#ifdef TTLDA_DOC_MAXNREG
+__global__ void __maxnreg__(TTLDA_DOC_MAXNREG) doc_pass_kernel(const EStepParams P)
+#else
+__global__ void __launch_bounds__(kDocThreads, (E <= 8 ? TTLDA_DOC_MINB : 1)) doc_pass_kernel(const EStepParams P)
+#endif
 {
     constexpr bool ESTEP = MODE > 0, REFRESH = MODE == 1;
     constexpr int R = 32 / G;
@@ -309,98 +319,6 @@ __global__ void __launch_bounds__(kDocThreads, 4) doc_pass_tma_kernel(const __gr
     }
 }
 
-// The same pass with the rows staged through a per-lane shared-memory ring by cp.async (ring_gather.cuh): kRingStages - 1
-// sub-batches in flight per warp without holding destination registers, one row buffer instead of two => 16 warps/SM.
-template <int G, int E, int MODE>
-__global__ void __launch_bounds__(kDocThreads, ring_min_ctas(E)) doc_pass_ring_kernel(const EStepParams P)
-{
-    constexpr bool ESTEP = MODE > 0, REFRESH = MODE == 1;
-    constexpr int R = 32 / G;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double* red = reinterpret_cast<double*>(smem_raw);  // 3*32 doubles for the CTA reduction (768 B)
-    unsigned char* wbase = smem_raw + 768 + (size_t)(threadIdx.x >> 5) * ring_bytes_per_warp<G, E>(P.ld);
-
-    const int lane = threadIdx.x & 31;
-    const int g = lane % G, r = lane / G;
-    const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    const int ld = (int)P.ld, K = P.K;
-    const bool last_ok = KSlice<G, E>::last_slice_ok(g, ld);
-    const uint64_t pol = l2_evict_first_policy();
-
-    RingPipe<G, E> pipe;
-    pipe.init(wbase, ld, g, r);
-    double* wbuf = reinterpret_cast<double*>(wbase);  // the epilogue's transpose buffer aliases the drained ring
-
-    double lga = 0., lg_asum = 0.;
-    if (REFRESH) {
-        for (int k = lane; k < K; k += 32) lga += lgamma(P.alpha_vec[k]);
-        lga = warp_sum(lga);
-        lg_asum = lgamma(P.alpha_sum);
-    }
-    double tok_acc = 0., theta_acc = 0., cnt_acc = 0.;
-    unsigned long long passes = 0, capped = 0;
-    const bool handoff = ESTEP && P.ratio_csc != nullptr;
-
-    for (int64_t d = warp0; d < P.D; d += nwarps) {
-        const int64_t b = P.rowptr[d], n = P.rowptr[d + 1] - b;
-        KSlice<G, E> t, acc;
-        t.load(P.eT_in + d * P.ld, g, last_ok);
-        acc.zero();
-        int c_cur = 0, c_nxt = 0, pos_cur = 0, pos_nxt = 0;  // per-item payload of the current / next 32-item batch
-        double my_p = 1.;
-        ring_walk<G, E>(
-            pipe, P.eB, ld, P.colidx + b, n, lane, g, r, last_ok, pol,
-            [&](int64_t base) {  // payload of the batch starting at item `base`
-                c_nxt = 0;
-                pos_nxt = 0;
-                if (base + lane < n) {
-                    c_nxt = ld_stream_s32(P.counts + b + base + lane, pol);
-                    if (handoff) pos_nxt = ld_stream_s32(reinterpret_cast<const int32_t*>(P.csr2csc) + b + base + lane, pol);
-                }
-            },
-            [&]() {
-                c_cur = c_nxt;
-                pos_cur = pos_nxt;
-            },
-            [&](int sb, const KSlice<G, E>& row) {
-                const int c = __shfl_sync(0xffffffffu, c_cur, sb * R + r);  // 0 past the end: the group idles
-                const double p = group_sum<G>(t.dot(row, ESTEP ? 1e-100 / G : 0.));  // lda_model.py:242
-                if (ESTEP) acc.axpy(fast_div_pos((double)c, p), row);                // lda_model.py:248
-                // hand p back to the lane that loaded nonzero `lane` of the batch (group lane % R, sub-batch lane / R)
-                const double pv = __shfl_sync(0xffffffffu, p, (lane % R) * G);
-                if (lane / R == sb) my_p = pv;
-            },
-            [&](int cnt) {
-                if (lane < cnt) {  // one log per nonzero (of theta.beta itself: the token term has no 1e-100, :125-139)
-                    tok_acc += (double)c_cur * log(ESTEP ? my_p - 1e-100 : my_p);
-                    cnt_acc += (double)c_cur;
-                    if (handoff) st_stream_f64(P.ratio_csc + (uint32_t)pos_cur, fast_div_pos((double)c_cur, my_p), pol);
-                }
-            });
-        if (ESTEP) {
-            __syncwarp();  // every lane is done with the ring before it becomes the transpose buffer
-            doc_epilogue<G, E, MODE>(P, d, acc, wbuf, lane, g, r, pol, lga, lg_asum, theta_acc, passes, capped);
-            __syncwarp();
-        }
-    }
-
-    double v[3] = {tok_acc, (lane == 0) ? theta_acc : 0., cnt_acc};
-    block_sum<3>(v, red);
-    if (threadIdx.x == 0) {
-        double* rec = P.records + (size_t)blockIdx.x * NPART;
-        rec[0] = v[0];
-        rec[1] = v[1];
-        rec[2] = v[2];
-#pragma unroll
-        for (int j = 3; j < NPART; ++j) rec[j] = 0.;
-    }
-    if (ESTEP && P.iters && lane == 0 && (passes | capped)) {
-        atomicAdd(P.iters, passes);
-        if (capped) atomicAdd(P.iters + 1, capped);
-    }
-}
-
 // PERSISTENT grid: exactly as many CTAs as are resident at once (occupancy x SMs), documents strided over their warps.
 // With more CTAs than fit (the usual "16 per SM"), a CTA retires only when its slowest warp is done — the other
 // warps' slots idle meanwhile — and every CTA pays its prologue / record epilogue: same-box A/B at cfg3, 16 CTAs/SM
@@ -437,22 +355,6 @@ static int launch_tma(const EStepParams& P, int* grid_out, int64_t table_rows, c
 }
 
 template <int G, int E, int MODE>
-static int launch_ring(const EStepParams& P, int* grid_out, cudaStream_t s)
-{
-    constexpr int R = 32 / G;
-    size_t per_warp = ring_bytes_per_warp<G, E>(P.ld);
-    const size_t smem = 768 + (kDocThreads / 32) * per_warp;
-    cudaError_t e = cudaFuncSetAttribute(doc_pass_ring_kernel<G, E, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(doc_pass_ring)");
-    (void)R;
-    const int grid = resident_grid(doc_pass_ring_kernel<G, E, MODE>, smem, P.D);
-    doc_pass_ring_kernel<G, E, MODE><<<grid, kDocThreads, smem, s>>>(P);
-    *grid_out = grid;
-    return TTLDA_OK;
-}
-
-template <int G, int E, int MODE>
 static int launch_shape(const EStepParams& P, int* grid_out, cudaStream_t s)
 {
     constexpr int R = 32 / G;
@@ -474,12 +376,6 @@ static int launch_doc_pass(const EStepParams& P, int64_t V, int* grid, cudaStrea
             const int E = (int)((P.ld + 2 * G - 1) / (2 * G));
             gs = {G, E};
         }
-    }
-    if (ring_gather_applicable(gs.G, gs.E) && ring_gather_enabled()) {  // rows staged through the cp.async ring
-#define TTLDA_CASE(GG, EE) \
-    if (gs.G == GG && gs.E == EE) return launch_ring<GG, EE, MODE>(P, grid, s);
-        TTLDA_FOR_EACH_RING_SHAPE(TTLDA_CASE)
-#undef TTLDA_CASE
     }
     if (tma_gather_applicable(gs.G, P.ld) && tma_gather_enabled() && V > 0) {  // rows fed by TMA gather4
         switch (gs.E) {

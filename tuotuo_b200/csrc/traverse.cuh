@@ -236,10 +236,4 @@ inline GroupShape group_shape_for(int64_t ld)
     X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                                               \
     X(32, 5) X(32, 6) X(32, 7) X(32, 8)
 
-// the shapes the cp.async ring feeds (ring_gather.cuh): every ld in (64, 1024]
-#define TTLDA_FOR_EACH_RING_SHAPE(X)                                                                 \
-    X(8, 5) X(8, 6) X(8, 7) X(8, 8)                                                                   \
-    X(16, 5) X(16, 6) X(16, 7) X(16, 8)                                                               \
-    X(32, 5) X(32, 6) X(32, 7) X(32, 8) X(32, 9) X(32, 10) X(32, 11) X(32, 12) X(32, 13) X(32, 14) X(32, 15) X(32, 16)
-
 }  // namespace ttlda
