@@ -12,7 +12,7 @@ lib = sys.argv[1] if len(sys.argv) > 1 else "tuotuo_b200/libttlda.so"
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 PATS = {"DMMA": r"\bDMMA", "UTMALDG": r"\bUTMALDG", "REDG.F64": r"\bREDG\.E\.ADD\.F64", "LDG.128": r"\bLDG\.E\.128",
         "LD.128(generic)": r"\bLD\.E\.128", "LDS.128": r"\bLDS\.128", "STG.128": r"\bSTG\.E\.128", "MUFU.RCP64H": r"MUFU\.RCP64H",
-        "DFMA": r"\bDFMA", "SHFL": r"\bSHFL", "ATOMG": r"\bATOMG", "BAR": r"\bBAR\.SYNC"}
+        "DFMA": r"\bDFMA", "SHFL": r"\bSHFL", "ATOMG": r"\bATOMG", "BAR": r"\bBAR\.SYNC", "LDGSTS": r"\bLDGSTS", "ATOMS": r"\bATOMS"}
 cur, counts, arch = None, collections.OrderedDict(), set()
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
