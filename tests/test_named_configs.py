@@ -258,3 +258,61 @@ def test_partial_fit_keeps_one_vocabulary_and_fitted_topics():
     fresh = np.random.gamma(100, 0.01, lam.shape)
     assert 0 < np.linalg.norm(lam - lam_fit) < 0.5 * np.linalg.norm(fresh - lam_fit)
     m.update_alpha()  # M is known on this path too
+
+
+@pytest.mark.parametrize("cfg", ["cfg3", "cfg4"])
+def test_full_size_properties(cfg):
+    """BASELINE.json configs[2] and configs[3] at FULL size (1M documents x 300 tokens, K = 100, V = 50k; 300k documents x
+    Poisson(330), K = 500, V = 102 660) — where no oracle can follow — through size-independent properties of the path:
+      * the mirror is the transpose of the CSR: csr2csc is a permutation, inside every (block, word) segment the documents
+        ascend, every entry's word matches its segment, the counts add up;
+      * sum_k (gamma_dk - alpha) = length of document d, for every document (lda_model.py:248 sums phi over k to 1);
+      * sum_wk (lambda_wk - eta) = number of tokens (lda_model.py:262-264); the token count of the ELBO record agrees;
+      * the perplexity bound decreases over the first EM iterations;
+      * a second fit of the same corpus reproduces gamma, lambda and every perplexity bit for bit."""
+    import torch
+
+    from tuotuo.lda_model import LDASmoothed
+    from tuotuo_b200.synth import CONFIGS, synthetic_document
+
+    dev = torch.device("cuda", 0)
+    D, L, K, V, pois = CONFIGS[cfg]
+    doc = synthetic_document(cfg, device=dev)
+    m = LDASmoothed(K, verbose=False)
+    perps = m.fit(doc, em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    st = m._st
+    c = st.corpus
+    assert c.D == D and c.V == V and c.nblocks > 1
+    if not pois:
+        assert c.tokens == D * L
+    # --- mirror = transpose
+    nnz = c.nnz
+    pos = c.csr2csc[:nnz].to(torch.int64)
+    seen = torch.zeros(nnz, dtype=torch.bool, device=dev)
+    seen[pos] = True
+    assert bool(seen.all())  # a permutation
+    del seen
+    seg = torch.searchsorted(c.colptr, torch.arange(nnz, device=dev), right=True) - 1  # (block, word) segment of a slot
+    word_of_slot = (seg % V).to(torch.int32)
+    assert torch.equal(word_of_slot[pos], c.colidx[:nnz])  # every entry sits in its own word's segment of its block
+    rows = torch.repeat_interleave(torch.arange(c.D, device=dev, dtype=torch.int32), torch.diff(c.rowptr))
+    assert torch.equal(c.docidx[:nnz][pos], rows)  # ... and the slot names its document
+    same = seg[1:] == seg[:-1]
+    assert bool((c.docidx[1:nnz][same] > c.docidx[:nnz - 1][same]).all())  # documents ascend inside a segment
+    del seg, word_of_slot, same, pos
+    # --- gamma rows and lambda total
+    lens = torch.zeros(c.D, dtype=torch.float64, device=dev)
+    lens.index_add_(0, rows.to(torch.int64), c.counts[:nnz].to(torch.float64))
+    alpha = float(np.asarray(m._alpha_).reshape(-1)[0])
+    assert float(((st.gamma[st.cur][:, :K].sum(1) - K * alpha) - lens).abs().max()) < 1e-8
+    m._sync_lambda()
+    tot = float((st.lam[:V, :K] - float(m._eta_)).sum())
+    assert abs(tot - c.tokens) / c.tokens < 1e-11
+    assert st.terms["count"] == c.tokens
+    assert perps[0] > perps[1] > perps[2] > perps[3]
+    # --- run-to-run reproducibility
+    g1, l1 = st.gamma[st.cur].clone(), st.lam.clone()
+    m2 = LDASmoothed(K, verbose=False)
+    perps2 = m2.fit(doc, em_num_step=3, update_hyper_parms=False, return_perplexities=True)
+    assert list(perps2) == list(perps)
+    assert torch.equal(m2._st.gamma[m2._st.cur], g1) and torch.equal(m2._st.lam, l1)
