@@ -334,6 +334,7 @@ class LDASmoothed:
 
     def _tokens(self):
         st, c = self._st, self._st.corpus
+        st.ev_corpus_free = None  # this pass reads the CSR arrays: a later streamed step must wait for it
         nv.elbo_tokens(c.rowptr, c.colidx, c.counts, st.K, st.eT[st.cur], st.eB, st.part[3], st.ws)
 
     def _estep_speculative(self, e_num_step: int, e_threshold: float = 1e-05):
@@ -341,6 +342,7 @@ class LDASmoothed:
         token term of the CURRENT state (part[0][0]), which completes its perplexity."""
         st, c = self._st, self._st.corpus
         cur, nxt = st.cur, st.cur ^ 1
+        st.ev_corpus_free = None  # reads the CSR arrays: a later streamed step must wait for it
         if self._inner_fixed_point:
             nv.estep_fixed_point(c.rowptr, c.colidx, c.counts, st.K, st.V, st.alpha_vec, self._alpha_sum(),
                                  st.eT[cur], st.eB, st.gamma[cur], st.gamma[nxt], st.eT[nxt], e_num_step,
@@ -567,7 +569,18 @@ class LDASmoothed:
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
         cs = self._copy_stream
-        cs.wait_stream(compute)  # the previous iteration may still be reading the corpus buffers
+        # The uploads overwrite the CSR arrays (or their compact staging buffers), which the previous step's widening,
+        # mirror and E-step kernels read — but not its statistics pass, theta refresh and M-step (they read the mirror, the
+        # ratios and the tables).  After a streamed step the uploads of the next one therefore wait for that step's last
+        # E-step only and cross PCIe underneath its statistics pass: with several ranks feeding from one host (8 GPUs:
+        # ~150 GB/s for all of them) the transfers, not the GPUs, pace the step, and this keeps the feed continuous
+        # across step boundaries.  After anything else the uploads wait for all queued work.
+        ev = getattr(st, "ev_corpus_free", None)
+        if ev is not None and os.environ.get("TTLDA_UPLOAD_OVERLAP", "1") == "1":
+            cs.wait_event(ev)
+        else:
+            cs.wait_stream(compute)
+        st.ev_corpus_free = None
         with torch.cuda.stream(cs):
             c.rowptr.copy_(rowptr, non_blocking=True)
         st.flags.zero_()
@@ -638,16 +651,23 @@ class LDASmoothed:
                 acc += st.part[0]
                 it_acc += st.iters
                 g0 = b + 1
+        if use_ratio:  # (without the ratio hand-off the statistics may rebuild the mirrored counts from the CSR arrays)
+            st.ev_corpus_free = torch.cuda.Event()
+            st.ev_corpus_free.record(compute)  # nothing queued from here on reads the CSR arrays / staging buffers
         c.nnz = nnz
         c.ccounts_valid = not use_ratio  # the mirrored counts are not rebuilt when the statistics use the ratios
         # one statistics pass over the whole mirror: its ticket order already walks the blocks one L2 window at a time,
         # and the GPU, not PCIe, bounds this step — per-block passes (ttlda_sstats_csc_block_f64) cost 2.3 ms more
         c.block_pos = plo
-        self._sstats_pass(st.eT[cur], st.ratio)
         st.part[0].copy_(acc)
         st.iters.copy_(it_acc)
+        # the record's device->host read is queued behind the last E-step, BEFORE the statistics pass: the host gets the
+        # perplexity terms (and the malformed-corpus flags) while that pass runs, and returns to the caller — whose next
+        # step's uploads then start underneath it
+        pending = self._collect_begin(tok_row=0)
+        self._sstats_pass(st.eT[cur], st.ratio)  # writes the statistics table and scratch only: nothing is committed yet
         try:
-            self.inner_iterations, capped = self._collect(tok_row=0)
+            self.inner_iterations, capped = self._collect_end(pending)
         except ValueError:
             # a malformed corpus was streamed in (and sanitised on the device): nothing was committed; go back to the
             # corpus the model was fitted on rather than keep the sanitised garbage as the state's corpus
