@@ -617,7 +617,8 @@ def run_ours(args):
     if args.strong and world > 1:  # the SAME corpus on every rank, cut into contiguous nnz-balanced document shards
         doc = synthetic_document(args.config, device=dev, seed=1234, docs=D).shard(rank, world)
     else:
-        doc = synthetic_document(args.config, device=dev, seed=1234 + rank, docs=D)
+        # weak scaling: every rank holds its own documents of ONE corpus (same topics, rank 0's shard is the N = 1 corpus)
+        doc = synthetic_document(args.config, device=dev, seed=1234, docs=D, doc_seed=(1234 + rank) if rank else None)
     main = measure(ctx, args.config, doc, K, V, args.steps, args.warmup, e2e=not args.no_e2e, fit_check=args.fit_check,
                    scaling="strong" if args.strong else "weak", traffic_key=args.config if not args.docs else None)
     main.setdefault("e2e", None)
@@ -665,7 +666,8 @@ def run_ours(args):
             if p["shard"]:  # the SAME corpus on every rank, cut into contiguous nnz-balanced document shards
                 dx = synthetic_document(p["config"], device=dev, seed=1234).shard(rank, world)
             else:
-                dx = synthetic_document(p["config"], device=dev, seed=1234 + rank, docs=p["docs"])
+                dx = synthetic_document(p["config"], device=dev, seed=1234, docs=p["docs"],
+                                        doc_seed=(1234 + rank) if rank else None)
                 if p["sampling"]:
                     dx.num_doc_population = Dx  # the population the sampled ELBO is scaled to (lda_model.py:152-153)
             r = measure(ctx, name, dx, Kx, Vx, xs, xw, sampling=p["sampling"], scaling=p["scaling"],

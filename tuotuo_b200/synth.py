@@ -24,8 +24,14 @@ CONFIGS = {
 
 
 def synthetic_token_stream(D: int, L: int, K: int, V: int, *, device, seed: int = 1234, poisson: bool = False,
-                           zipf_s: float = 1.0, chunk_docs: int = 65536):
-    """Returns (token_ids int32[T], doc_offsets int64[D+1]) on `device`."""
+                           zipf_s: float = 1.0, chunk_docs: int = 65536, doc_seed: int | None = None):
+    """Returns (token_ids int32[T], doc_offsets int64[D+1]) on `device`.
+
+    `seed` fixes the generative MODEL (the topics beta and the vocabulary permutation) and, when `doc_seed` is None, the
+    documents drawn from it (one stream, as always).  `doc_seed` draws the documents from their own stream instead:
+    document shards of ONE corpus (same model, different documents) for weak-scaling runs — with a different `seed` per
+    rank every rank would hold a different model, and shards whose distinct-words-per-document differ by several percent
+    (measured: 203.7M ... 218.2M nonzeros for 1M x 300-token documents), i.e. unequal work for equal token counts."""
     dev = torch.device(device)
     g = torch.Generator(device=dev)
     g.manual_seed(seed)
@@ -38,6 +44,9 @@ def synthetic_token_stream(D: int, L: int, K: int, V: int, *, device, seed: int 
     cdf = torch.cumsum(beta, 1)
     cdf[:, -1] = 1.0
     cdf_flat = (cdf + torch.arange(K, dtype=torch.float64, device=dev)[:, None]).reshape(-1)
+    if doc_seed is not None:
+        g = torch.Generator(device=dev)
+        g.manual_seed(doc_seed)
 
     if poisson:
         lens = torch.poisson(torch.full((D,), float(L), device=dev), generator=g).to(torch.int64).clamp_(min=1)
@@ -65,9 +74,11 @@ def synthetic_token_stream(D: int, L: int, K: int, V: int, *, device, seed: int 
     return tokens, offs
 
 
-def synthetic_document(name_or_shape, *, device, seed: int = 1234, docs: int | None = None) -> Document:
+def synthetic_document(name_or_shape, *, device, seed: int = 1234, docs: int | None = None,
+                       doc_seed: int | None = None) -> Document:
     """A ``Document`` for one of the BASELINE.json configurations ("cfg2", "cfg3", ...) or a (D, L, K, V) tuple.
-    `docs` overrides the number of documents (shards / bounded samples keep the K, V, L of the configuration)."""
+    `docs` overrides the number of documents (shards / bounded samples keep the K, V, L of the configuration);
+    `doc_seed`: the documents' own random stream (synthetic_token_stream), for shards of one corpus."""
     if isinstance(name_or_shape, str):
         D, L, K, V, pois = CONFIGS[name_or_shape]
     else:
@@ -75,9 +86,9 @@ def synthetic_document(name_or_shape, *, device, seed: int = 1234, docs: int | N
         pois = False
     if docs is not None:
         D = int(docs)
-    tok, offs = synthetic_token_stream(D, L, K, V, device=device, seed=seed, poisson=pois)
+    tok, offs = synthetic_token_stream(D, L, K, V, device=device, seed=seed, poisson=pois, doc_seed=doc_seed)
     doc = Document.from_token_ids(tok, offs, V)
-    doc.config = dict(D=D, L=L, K=K, V=V, poisson=pois, seed=seed)
+    doc.config = dict(D=D, L=L, K=K, V=V, poisson=pois, seed=seed, doc_seed=doc_seed)
     return doc
 
 
