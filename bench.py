@@ -8,11 +8,12 @@
 A "step" is ONE full EM iteration of the hot path over the resident corpus, made through the PUBLIC call
 `LDASmoothed.em_iteration()` — the body of `LDASmoothed.fit`'s loop, which `fit` itself calls: E-step (gamma, with the
 ELBO token term of the incoming state as a by-product of the same dot products), the device->host read of the
-perplexity terms and the host-side convergence test, K x V sufficient statistics, [NCCL all-reduce of the statistics
-when N > 1], theta refresh, M-step (lambda + beta refresh); every step yields one perplexity.  Workload at N=1:
-BASELINE.json configs[2] "synthetic 1M docs x 300 tokens, K=100, V=50k" (cfg3), the configuration the roofline target
-is quoted on; for N > 1 every rank holds its own cfg3-sized document shard (weak scaling), lambda is replicated and
-the statistics are summed with one fp64 all-reduce per iteration.
+perplexity terms and the host-side convergence test, K x V sufficient statistics, [their exchange across ranks, fused
+into the vocabulary-sharded M-step, when N > 1], theta refresh, M-step (lambda + beta refresh); every step yields one
+perplexity.  Workload at N=1: BASELINE.json configs[2] "synthetic 1M docs x 300 tokens, K=100, V=50k" (cfg3), the
+configuration the roofline target is quoted on; for N > 1 every rank holds its own cfg3-sized shard of documents drawn
+from the SAME generative model (weak scaling: rank 0's shard is the N=1 corpus), exp(E[log beta]) is replicated and lambda
+sharded over the vocabulary.
 
 Prints ONE JSON line (rank 0).  `value` is the device-timed whole-job throughput with the corpus resident in HBM;
 `e2e` repeats the measurement through `LDASmoothed.em_step_from_host` with the CSR corpus coming from pinned HOST
@@ -685,7 +686,10 @@ def run_ours(args):
                 "config": {"workload": f"{args.config}: {main['docs']} docs x ~{L} tokens, K={K}, V={V} "
                                        f"({main['docs'] // world} docs per GPU), batch VI EM iteration",
                            "docs": main["docs"], "doc_tokens": main["doc_tokens"], "nnz": main["nnz"], "K": K, "V": V,
-                           "parallelism": f"doc-shard x{world}" + (" + NCCL all-reduce(K*V f64)" if world > 1 else ""),
+                           "parallelism": f"doc-shard x{world}" + (
+                               f" + K*V statistics exchange ({os.environ.get('TTLDA_MSTEP', 'peer')}: fused into the "
+                               "vocabulary-sharded M-step over NVLink peer memory / NVSwitch multicast; nccl: "
+                               "reduce-scatter + all-gather; replicated: all-reduce)" if world > 1 else ""),
                            "sstats": args.sstats, "doc_blocks": main["doc_blocks"],
                            "api": "LDASmoothed.em_iteration() — the loop body fit() calls",
                            "elbo": "token term fused into the E-step (16K-byte-per-nonzero variant, SURVEY 8d)",
