@@ -1,4 +1,5 @@
 # round 2, call M: slice-walk mirror v2 (plain 16-bit counters + atomic redo, coalesced colptr scan, slice-staged placement),
+# (provenance of profiles/r02m_* / r02vw_*: the variants measured here were removed from the product afterwards — tools/experiments/estep_row_pipelines.cuh)
 # cp.async ring-fed E-step A/B at cfg3 / cfg4 / cfg5 shard
 set -x
 O=gpurun_out/r02m

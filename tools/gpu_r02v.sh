@@ -1,4 +1,5 @@
 # round 2, call V: E-step occupancy A/B at cfg3 — 1-warp CTAs with a register cap (13 / 14 / 15 warps per SM at 152 / 144 /
+# (provenance of profiles/r02m_* / r02vw_*: the variants measured here were removed from the product afterwards — tools/experiments/estep_row_pipelines.cuh)
 # 136 registers, small spills) against the 3 x 4-warp baseline (12 warps, 166 registers), same box
 set -x
 O=gpurun_out/r02v

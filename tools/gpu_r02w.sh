@@ -1,4 +1,5 @@
 # round 2, call W: deep register pipelines in the E-step (TTLDA_SKEW=3: three row buffers, two sub-batches in flight, 10 one-warp
+# (provenance of profiles/r02m_* / r02vw_*: the variants measured here were removed from the product afterwards — tools/experiments/estep_row_pipelines.cuh)
 # CTAs per SM; =4: four buffers + skewed chain, 9 per SM) against the default walk (two buffers, 12 warps), same box
 set -x
 O=gpurun_out/r02w
