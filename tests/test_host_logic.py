@@ -193,3 +193,34 @@ def test_corpus_tokenizer_equals_per_document_pipeline():
     d = Document({i: t for i, t in enumerate(texts[:50])})
     assert d.sample_docs_list == [text_pipeline(t).split(" ") for t in texts[:50]]
     assert d.M == 50 and d.V == len(d.vocab_to_idx)
+
+
+def test_synthetic_shards_share_one_model():
+    """synthetic_token_stream: `seed` fixes the generative model, `doc_seed` the documents drawn from it.  Weak-scaling
+    shards (bench.py, N > 1) are documents of ONE corpus: same topics, different documents, statistically equal work
+    per rank; doc_seed=None keeps the single-stream corpus every N = 1 number was measured on."""
+    import torch
+
+    from tuotuo_b200.synth import synthetic_token_stream
+
+    D, L, K, V = 3000, 60, 8, 4000
+    a = synthetic_token_stream(D, L, K, V, device="cpu", seed=11)
+    b = synthetic_token_stream(D, L, K, V, device="cpu", seed=11, doc_seed=None)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    shards = [synthetic_token_stream(D, L, K, V, device="cpu", seed=11, doc_seed=100 + r)[0] for r in range(3)]
+    assert not torch.equal(shards[0], shards[1]) and not torch.equal(shards[0], a[0])
+    other_model = synthetic_token_stream(D, L, K, V, device="cpu", seed=12, doc_seed=100)[0]
+
+    def profile(tok):  # corpus-wide word frequencies: a fingerprint of the topics, not of the documents
+        return torch.bincount(tok.to(torch.int64), minlength=V).to(torch.float64) / tok.numel()
+
+    same = float((profile(shards[0]) - profile(shards[1])).abs().sum())
+    diff = float((profile(shards[0]) - profile(other_model)).abs().sum())
+    assert same < 0.25 * diff  # shards of one model agree far better than two models do
+
+    def distinct_per_doc(tok):
+        t = tok.view(D, L).to(torch.int64)
+        return float((torch.sort(t, 1).values.diff(dim=1) != 0).sum(1).add(1).double().mean())
+
+    d = [distinct_per_doc(s) for s in shards]
+    assert max(d) / min(d) < 1.01  # equal nonzeros per document = equal work per rank
