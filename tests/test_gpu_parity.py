@@ -636,8 +636,8 @@ def test_slice_walk_mirror_equals_sorted_mirror(monkeypatch, dev, case):
     ccounts / csr2csc, bit for bit, as the generic CUB pair sort (TTLDA_CSC_WALK=0) and as a stable NumPy argsort: ragged
     and empty documents, several document blocks, a vocabulary that leaves one CTA per SM, documents longer than one walk
     step (> 256 entries) and longer than a whole stage buffer, slices of more than one 256-document offsets chunk, many
-    small slices (generic placement), and a vocabulary beyond the counter table (V > 112 000: both settings run the
-    generic path)."""
+    small slices (generic placement), and a vocabulary beyond one counter table (V = 120 000: two word ranges, one walk
+    CTA per (slice, range))."""
     from tuotuo_b200.corpus import DeviceCorpus
     from tuotuo_b200.synth import numpy_corpus
 
